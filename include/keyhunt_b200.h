@@ -1,0 +1,129 @@
+/* keyhunt_b200.h — C ABI of libkh_b200.so: the B200-native replacement for keyhunt's per-thread
+ * key-range search workers.
+ *
+ * The reference (naanprofit/keyhunt) has no FFI boundary: its workers are pthread entry points that
+ * read process globals.  This header is the boundary a maintainer binds instead of spawning those
+ * threads (see INTEGRATION.md for the exact patch against keyhunt.cpp).  Each entry point names the
+ * reference code it replaces (file:line relative to the reference root).
+ *
+ * Conventions: extern "C", opaque handle, plain pointers + sizes, caller owns every host buffer, the
+ * library owns device memory.  Return 0 on success, a negative KH_E* code on failure (message via
+ * kh_last_error).  One host thread per context (= per GPU); calls on one context are not re-entrant.
+ * 256-bit integers cross the boundary as 32-byte BIG-ENDIAN strings (Int::Get32Bytes, Int.cpp:308).
+ * There is no CPU fallback: kh_create fails when no CUDA device is usable.
+ */
+#ifndef KEYHUNT_B200_H
+#define KEYHUNT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KH_OK 0
+#define KH_ENODEV (-1)   /* no usable CUDA device / CUDA runtime error */
+#define KH_EINVAL (-2)   /* bad argument (range not a multiple of 1024, n not 2^even, ...) */
+#define KH_ENOMEM (-3)   /* device or host allocation failed */
+#define KH_ESTATE (-4)   /* call out of order (scan before set_targets, search before build, ...) */
+#define KH_EOVERFLOW (-5)/* more hits than the hit buffer holds (hits were dropped) */
+
+typedef struct kh_ctx kh_ctx;
+
+/* FLAGMODE / FLAGCRYPTO / FLAGSEARCH values of the reference (keyhunt.cpp:55-68) */
+enum { KH_MODE_XPOINT = 0, KH_MODE_ADDRESS = 1, KH_MODE_BSGS = 2, KH_MODE_RMD160 = 3 };
+enum { KH_CRYPTO_BTC = 1, KH_CRYPTO_ETH = 2 };
+enum { KH_SEARCH_UNCOMPRESS = 0, KH_SEARCH_COMPRESS = 1, KH_SEARCH_BOTH = 2 };
+/* which derived value matched */
+enum { KH_HIT_COMP02 = 0, KH_HIT_COMP03 = 1, KH_HIT_UNCOMP = 2, KH_HIT_ETH = 3, KH_HIT_XPOINT = 4 };
+
+/* context: cudaSetDevice, stream, hit buffer.  (replaces nothing: the reference is one process) */
+int kh_create(kh_ctx **out, int device_ordinal);
+void kh_destroy(kh_ctx *ctx);
+const char *kh_last_error(kh_ctx *ctx);
+/* tunables: "threads_per_sm" (walker threads per SM), "steps_per_launch", "hit_capacity" */
+int kh_set_option(kh_ctx *ctx, const char *name, int64_t value);
+
+/* bloom_init2 sizing (bloom/bloom.cpp:154-187) with error = 0.000001 (keyhunt.cpp:7620) */
+typedef struct {
+  uint64_t entries, bits, bytes;
+  uint32_t hashes;
+  uint32_t pad;
+} kh_bloom_desc;
+int kh_bloom_params(uint64_t entries, kh_bloom_desc *out);
+
+/* ---- scan modes: replaces thread_process (keyhunt.cpp:3265-3861) --------------------------------- */
+
+/* Target set = what readFileAddress leaves in `bloom` + `addressTable` (keyhunt.cpp:7033-7470,
+ * _sort :4307): N raw 20-byte records in any order.  The library sorts them, uploads them and sets
+ * the bloom bits on the device (bit-identical to bloom_add per record).  If bloom_bits != NULL it is
+ * used as the bloom image instead (desc must describe it).  entries = N<=10000 ? 10000 : N unless
+ * desc overrides it (keyhunt.cpp:7608). */
+int kh_set_targets(kh_ctx *ctx, int mode, int crypto, int search, const uint8_t *records20, uint64_t n_records,
+                   const kh_bloom_desc *desc, const uint8_t *bloom_bits);
+/* read back the device-resident bloom image / sorted table (parity checks, -S style persistence) */
+int kh_get_bloom(kh_ctx *ctx, kh_bloom_desc *desc, uint8_t *dst, uint64_t cap_bytes);
+int kh_get_table(kh_ctx *ctx, uint8_t *dst20, uint64_t cap_records, uint64_t *n_records);
+
+/* Scans the keys start + i*stride, i in [0, n_points); n_points must be a multiple of 1024 (one
+ * reference batch).  This is what a worker does for its claimed chunk (keyhunt.cpp:3321-3324,
+ * :3348-3856) — the caller keeps the range cursor and the chunk overshoot rule.
+ * Blocking; hits accumulate in the context until polled. */
+int kh_scan(kh_ctx *ctx, const uint8_t start_be[32], const uint8_t stride_be[32], uint64_t n_points);
+
+typedef struct {
+  uint8_t key_be[32];    /* reported private key, after the n-k fix-up of keyhunt.cpp:3629-3635 */
+  uint8_t pub_x[32];     /* public key of key_be */
+  uint8_t pub_y[32];
+  uint8_t matched[20];   /* the 20 bytes found in the table */
+  uint8_t kind;          /* KH_HIT_* */
+  uint8_t pad[3];
+  uint64_t index;        /* point index inside the scanned range */
+} kh_hit;
+/* drains the hits of the scans since the last poll, ascending (index, kind); *n = number written.
+ * Returns KH_EOVERFLOW if the device hit buffer overflowed. */
+int kh_poll_hits(kh_ctx *ctx, kh_hit *out, int max, int *n);
+
+/* per-key derivation on the device (hit fix-up / writekey: keyhunt.cpp:3629, :6891, :6925):
+ * public key, both hash160 forms, ETH address */
+typedef struct {
+  uint8_t pub_x[32], pub_y[32];
+  uint8_t h160_comp[20], h160_uncomp[20], eth[20];
+  uint8_t pad[4];
+} kh_keyinfo;
+int kh_derive(kh_ctx *ctx, const uint8_t *keys_be, uint64_t n_keys, kh_keyinfo *out);
+
+/* ---- BSGS: replaces thread_bPload (keyhunt.cpp:5284), bsgs_sort (:4412), thread_process_bsgs (:4549),
+ *      bsgs_secondcheck (:5151), bsgs_thirdcheck (:5186), bsgs_searchbinary (:4510) -------------------- */
+typedef struct {
+  uint64_t n, m, m2, m3, aux;          /* BSGS_N (rounded), bsgs_m, bsgs_m2, bsgs_m3, bsgs_aux */
+  kh_bloom_desc tier[3];               /* per-shard descriptors of bloom_bP / bloom_bPx2nd / bloom_bPx3rd */
+} kh_bsgs_desc;
+/* n = -n value (2^even >= 2^20), k = -k factor.  Builds the 3 x 256 bloom shards and the sorted bP
+ * table on the device; everything stays resident in HBM. */
+int kh_bsgs_build(kh_ctx *ctx, uint64_t n, uint32_t k);
+int kh_bsgs_describe(kh_ctx *ctx, kh_bsgs_desc *out);
+/* tier 1..3: bf bytes of one shard; tier 0: the bP table (m3 x 16-byte struct bsgs_xvalue, shard ignored) */
+int kh_bsgs_export(kh_ctx *ctx, int tier, int shard, void *dst, uint64_t cap_bytes);
+int kh_bsgs_import(kh_ctx *ctx, int tier, int shard, const void *src, uint64_t len_bytes);
+/* sequential search (-B sequential) of [start, end) for one public key, in windows of 2n keys like
+ * thread_process_bsgs; *found = 1 and the key when found. */
+int kh_bsgs_search(kh_ctx *ctx, const uint8_t pub_xy_be[64], const uint8_t start_be[32], const uint8_t end_be[32],
+                   uint8_t found_key_be[32], int *found);
+
+/* ---- measurement -------------------------------------------------------------------------------- */
+typedef struct {
+  double walk_ms;          /* device time of the walk kernels (CUDA events on the context stream) */
+  double setup_ms;         /* device time of table/centre set-up kernels */
+  double aux_ms;           /* BSGS refine / sort / bloom-build kernels */
+  uint64_t walk_launches;  /* kernels launched */
+  uint64_t other_launches;
+  uint64_t points;         /* points (scan) or giant steps (bsgs) or baby steps (build) walked */
+  uint64_t walker_threads; /* T of the last walk */
+  uint64_t tier1_positives;/* BSGS: tier-1 bloom positives sent to refinement */
+} kh_stats;
+int kh_get_stats(kh_ctx *ctx, kh_stats *out, int reset);
+int kh_device_info(kh_ctx *ctx, char *name, int name_cap, int *sm_count, uint64_t *hbm_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

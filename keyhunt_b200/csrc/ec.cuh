@@ -1,0 +1,202 @@
+// ec.cuh — secp256k1 group operations used OUTSIDE the batch inner loop (set-up of the G-multiple
+// tables and thread start points, hit derivation, BSGS refinement).  The inner loop itself
+// (affine P +- i*G with a shared Montgomery inverse) lives in walk.cuh.
+//
+// Replaces Secp256K1::ComputePublicKey / ScalarBaseMultiplication (SECP256K1.cpp:205, :702),
+// AddDirect (:455), DoubleDirect (:589), Negation (:316).  The reference uses a wNAF-7 table; here
+// every thread that needs k*G does a plain Jacobian double-and-add (set-up cost only, off the hot
+// path) and one field inversion.
+#pragma once
+#include "fe.cuh"
+
+namespace kh {
+
+struct ge {   // affine point; inf != 0 means the point at infinity
+  fe x, y;
+  uint32_t inf;
+};
+struct gej {  // Jacobian
+  fe x, y, z;
+  uint32_t inf;
+};
+
+struct u256 {  // plain 256-bit integer (scalars / private keys), little-endian limbs
+  uint32_t v[8];
+};
+
+// Generator (SECP256K1.cpp:161-162), limbs little-endian
+#define KH_GX {0x16F81798u, 0x59F2815Bu, 0x2DCE28D9u, 0x029BFCDBu, 0xCE870B07u, 0x55A06295u, 0xF9DCBBACu, 0x79BE667Eu}
+#define KH_GY {0xFB10D4B8u, 0x9C47D08Fu, 0xA6855419u, 0xFD17B448u, 0x0E1108A8u, 0x5DA4FBFCu, 0x26A3C465u, 0x483ADA77u}
+
+KH_HD void ge_set_g(ge &g) {
+  const uint32_t gx[8] = KH_GX, gy[8] = KH_GY;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { g.x.v[i] = gx[i]; g.y.v[i] = gy[i]; }
+  g.inf = 0;
+}
+
+// ---- plain 256-bit integers ------------------------------------------------------------------------
+KH_HD void u256_from_be(u256 &r, const uint8_t *b) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t *p = b + 4 * (7 - i);
+    r.v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+  }
+}
+KH_HD void u256_to_be(uint8_t *b, const u256 &a) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t *p = b + 4 * (7 - i);
+    p[0] = (uint8_t)(a.v[i] >> 24); p[1] = (uint8_t)(a.v[i] >> 16); p[2] = (uint8_t)(a.v[i] >> 8); p[3] = (uint8_t)a.v[i];
+  }
+}
+// r = a + b*m (mod 2^256), m 64-bit
+KH_HD void u256_add_mul64(u256 &r, const u256 &a, const u256 &b, uint64_t m) {
+  const uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+  // t = b * m (truncated), schoolbook with 64-bit temporaries (set-up path only)
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += (uint64_t)b.v[i] * m0; t[i] = (uint32_t)c; c >>= 32; }
+  c = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) { c += (uint64_t)b.v[i] * m1 + t[i + 1]; t[i + 1] = (uint32_t)c; c >>= 32; }
+  c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + t[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+}
+// curve order n (SECP256K1.cpp:164)
+#define KH_N {0xD0364141u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}
+// r = n - a   (Int::Neg + Add(order), keyhunt.cpp:3632-3633)
+KH_HD void u256_neg_mod_n(u256 &r, const u256 &a) {
+  const uint32_t n[8] = KH_N;
+  kh_sub8(r.v, n, a.v);
+}
+
+// ---- Jacobian arithmetic (a = 0) ---------------------------------------------------------------------
+KH_HD void gej_set_inf(gej &r) { r.inf = 1; fe_set_zero(r.x); fe_set_zero(r.y); fe_set_zero(r.z); }
+
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+void gej_double(gej &r, const gej &p) {
+  if (p.inf || fe_is_zero(p.y)) { gej_set_inf(r); return; }
+  fe a, b, c, d, e, f, t;
+  fe_sqr(a, p.x);
+  fe_sqr(b, p.y);
+  fe_sqr(c, b);
+  fe_add(t, p.x, b); fe_sqr(t, t); fe_sub(t, t, a); fe_sub(t, t, c); fe_add(d, t, t);
+  fe_add(e, a, a); fe_add(e, e, a);
+  fe_sqr(f, e);
+  gej o; o.inf = 0;
+  fe_mul(o.z, p.y, p.z); fe_add(o.z, o.z, o.z);
+  fe_sub(o.x, f, d); fe_sub(o.x, o.x, d);
+  fe_sub(t, d, o.x); fe_mul(o.y, e, t);
+  fe_add(c, c, c); fe_add(c, c, c); fe_add(c, c, c);
+  fe_sub(o.y, o.y, c);
+  r = o;
+}
+
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+void gej_add_ge(gej &r, const gej &p, const ge &q) {
+  if (q.inf) { r = p; return; }
+  if (p.inf) { r.x = q.x; r.y = q.y; fe_set_u32(r.z, 1); r.inf = 0; return; }
+  fe z2, u2, s2, h, rr, h2, h3, t;
+  fe_sqr(z2, p.z);
+  fe_mul(u2, q.x, z2);
+  fe_mul(s2, q.y, p.z); fe_mul(s2, s2, z2);
+  fe_sub(h, u2, p.x);
+  fe_sub(rr, s2, p.y);
+  if (fe_is_zero(h)) {
+    if (fe_is_zero(rr)) { gej_double(r, p); return; }
+    gej_set_inf(r); return;
+  }
+  fe_sqr(h2, h); fe_mul(h3, h2, h);
+  gej o; o.inf = 0;
+  fe_mul(t, p.x, h2);
+  fe_sqr(o.x, rr); fe_sub(o.x, o.x, h3); fe_sub(o.x, o.x, t); fe_sub(o.x, o.x, t);
+  fe_sub(t, t, o.x); fe_mul(o.y, rr, t);
+  fe_mul(t, p.y, h3); fe_sub(o.y, o.y, t);
+  fe_mul(o.z, p.z, h);
+  r = o;
+}
+
+KH_HD void gej_to_ge(ge &r, const gej &p) {
+  if (p.inf) { r.inf = 1; fe_set_zero(r.x); fe_set_zero(r.y); return; }
+  fe zi, zi2, zi3;
+  fe_inv(zi, p.z); fe_sqr(zi2, zi); fe_mul(zi3, zi2, zi);
+  fe_mul(r.x, p.x, zi2); fe_mul(r.y, p.y, zi3);
+  r.inf = 0;
+}
+
+// r = k * base  (double-and-add, MSB first; k is any 256-bit integer)
+KH_HD void ge_scalar_mul(ge &r, const ge &base, const u256 &k) {
+  gej acc;
+  gej_set_inf(acc);
+#pragma unroll 1
+  for (int i = 255; i >= 0; i--) {
+    gej_double(acc, acc);
+    if ((k.v[i >> 5] >> (i & 31)) & 1) gej_add_ge(acc, acc, base);
+  }
+  gej_to_ge(r, acc);
+}
+KH_HD void ge_mul_g(ge &r, const u256 &k) {
+  ge g;
+  ge_set_g(g);
+  ge_scalar_mul(r, g, k);
+}
+KH_HD void ge_neg(ge &r, const ge &p) { r.x = p.x; fe_neg(r.y, p.y); r.inf = p.inf; }
+// full affine addition with every special case (used for start points: Q + k*G)
+KH_HD void ge_add(ge &r, const ge &p, const ge &q) {
+  gej j;
+  j.x = p.x; j.y = p.y; fe_set_u32(j.z, 1); j.inf = p.inf;
+  gej s;
+  gej_add_ge(s, j, q);
+  gej_to_ge(r, s);
+}
+
+// Secp256K1::AddDirect (SECP256K1.cpp:455) exactly as the reference computes it: no special cases,
+// and an unusable difference (dx = 0) yields inv = 0 and therefore the same deterministic garbage
+// the reference produces.  Used by the BSGS tier checks so that they agree with the reference even
+// on its degenerate inputs.
+KH_HD void ge_add_direct(ge &r, const ge &p1, const ge &p2) {
+  fe dy, dx, s, p, t;
+  fe_sub(dy, p2.y, p1.y);
+  fe_sub(dx, p2.x, p1.x);
+  fe_inv(dx, dx);
+  fe_mul(s, dy, dx);
+  fe_sqr(p, s);
+  ge o;
+  fe_sub(o.x, p, p1.x);
+  fe_sub(o.x, o.x, p2.x);
+  fe_sub(t, p2.x, o.x);
+  fe_mul(o.y, t, s);
+  fe_sub(o.y, o.y, p2.y);
+  o.inf = 0;
+  r = o;
+}
+// r = a + b, r = a - b for a small b (keys near a base key)
+KH_HD void u256_add_u64(u256 &r, const u256 &a, uint64_t b) {
+  uint64_t c = b;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; if (i == 0) c += 0; }
+}
+KH_HD void u256_sub_u64(u256 &r, const u256 &a, uint64_t b) {
+  uint32_t bb[8] = {(uint32_t)b, (uint32_t)(b >> 32), 0, 0, 0, 0, 0, 0};
+  kh_sub8(r.v, a.v, bb);
+}
+KH_HD void u256_set_u64(u256 &r, uint64_t b) {
+  r.v[0] = (uint32_t)b; r.v[1] = (uint32_t)(b >> 32);
+#pragma unroll
+  for (int i = 2; i < 8; i++) r.v[i] = 0;
+}
+
+}  // namespace kh

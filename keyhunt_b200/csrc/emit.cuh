@@ -1,0 +1,169 @@
+// emit.cuh — what happens to each point the walk produces: hash -> bloom probe -> sorted-table
+// search -> hit record.  Device form of loop C of thread_process (keyhunt.cpp:3475-3830), of the
+// tier-1 probe of thread_process_bsgs (:4819-4823) and of the per-point body of thread_bPload
+// (:5394-5443).
+#pragma once
+#include <stdint.h>
+
+#include "bloom.cuh"
+#include "walk.cuh"
+
+namespace kh {
+
+// raw device-side records; the host turns them into kh_hit (private key, n-k fix-up, public key)
+enum { KH_KIND_COMP02 = 0, KH_KIND_COMP03 = 1, KH_KIND_UNCOMP = 2, KH_KIND_ETH = 3, KH_KIND_XPOINT = 4 };
+
+struct RawHit {
+  uint64_t batch;
+  uint32_t idx;
+  uint32_t kind;
+  uint32_t h[5];   // matched 20 bytes as LE words
+  uint32_t pad;
+};
+
+struct HitSink {
+  RawHit *hits;
+  uint32_t *count;   // total hits produced (may exceed cap; the excess is dropped and reported)
+  uint32_t cap;
+  uint32_t pad;
+};
+
+KH_HD uint32_t kh_atomic_inc(uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, 1u);
+#else
+  return (*p)++;
+#endif
+}
+KH_HD void sink_push(const HitSink &s, uint64_t batch, uint32_t idx, uint32_t kind, const uint32_t h[5]) {
+  uint32_t slot = kh_atomic_inc(s.count);
+  if (slot < s.cap) {
+    RawHit r;
+    r.batch = batch; r.idx = idx; r.kind = kind; r.pad = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.h[i] = h[i];
+    s.hits[slot] = r;
+  }
+}
+
+// ---- scan modes ------------------------------------------------------------------------------------
+enum { KH_SCAN_XPOINT = 0, KH_SCAN_COMP = 1, KH_SCAN_UNCOMP = 2, KH_SCAN_BOTH = 3, KH_SCAN_ETH = 4 };
+
+struct ScanTargets {
+  BloomDev bloom;
+  const uint32_t *table;   // N x 5 big-endian-packed words, ascending
+  uint64_t n;
+  HitSink sink;
+};
+
+template <int KIND>
+struct ScanEmit {
+  static constexpr bool NEED_Y = (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH || KIND == KH_SCAN_ETH);  // keyhunt.cpp:3294
+  const ScanTargets &tg;
+  KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
+
+  KH_HDM void probe(const uint32_t h[5], uint32_t kind, uint64_t batch, uint32_t idx) {
+    if (bloom_check20(tg.bloom, h)) {                  // keyhunt.cpp:3621
+      if (table_contains(tg.table, tg.n, h))           // keyhunt.cpp:3623
+        sink_push(tg.sink, batch, idx, kind, h);
+    }
+  }
+  KH_HDM void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
+    uint32_t h[5];
+    if (KIND == KH_SCAN_XPOINT) {                      // keyhunt.cpp:3810-3821 (first 20 bytes of X)
+#pragma unroll
+      for (int i = 0; i < 5; i++) h[i] = bswap32(x.v[7 - i]);
+      probe(h, KH_KIND_XPOINT, batch, idx);
+    }
+    if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_BOTH) {  // both prefixes for every X, keyhunt.cpp:3493-3494
+#pragma unroll 1
+      for (uint32_t pre = 2; pre <= 3; pre++) {
+        hash160_compressed(h, pre, x);
+        probe(h, pre == 2 ? KH_KIND_COMP02 : KH_KIND_COMP03, batch, idx);
+      }
+    }
+    if (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {  // keyhunt.cpp:3519
+      hash160_uncompressed(h, x, y);
+      probe(h, KH_KIND_UNCOMP, batch, idx);
+    }
+    if (KIND == KH_SCAN_ETH) {                           // keyhunt.cpp:3540
+      eth_address(h, x, y);
+      probe(h, KH_KIND_ETH, batch, idx);
+    }
+  }
+};
+
+// ---- BSGS ------------------------------------------------------------------------------------------
+struct BpEntry {          // == struct bsgs_xvalue (keyhunt.cpp:132): 6 key bytes, 2 pad, u64 index
+  uint8_t value[6];
+  uint8_t pad[2];
+  uint64_t index;
+};
+
+struct BsgsTables {
+  BloomDev tier[3];       // bloom_bP, bloom_bPx2nd, bloom_bPx3rd: 256 shards each, shard = X[0]
+  BpEntry *table;         // m3 entries
+  uint64_t m, m2, m3;
+};
+
+// baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
+struct BabyEmit {
+  static constexpr bool NEED_Y = false;
+  const BsgsTables &bt;
+  KH_HDM explicit BabyEmit(const BsgsTables &b) : bt(b) {}
+  KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
+    const uint64_t p = batch * KH_GRP + idx;
+    if (p >= bt.m) return;
+    uint32_t w[8];
+    fe_to_le_words(w, x);
+    const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);
+    const uint64_t b = xxh64_32(w, a);
+    const uint32_t shard = x.v[7] >> 24;               // first byte of the big-endian X
+    if (p < bt.m3) {
+      BpEntry en;
+      // X bytes 16..21 = limb 3 (bytes 16..19) and the top half of limb 2 (bytes 20,21)
+      en.value[0] = (uint8_t)(x.v[3] >> 24); en.value[1] = (uint8_t)(x.v[3] >> 16);
+      en.value[2] = (uint8_t)(x.v[3] >> 8);  en.value[3] = (uint8_t)(x.v[3]);
+      en.value[4] = (uint8_t)(x.v[2] >> 24); en.value[5] = (uint8_t)(x.v[2] >> 16);
+      en.pad[0] = 0; en.pad[1] = 0;
+      en.index = p;
+      bt.table[p] = en;
+      bloom_set(bt.tier[2], shard, a, b);
+    }
+    if (p < bt.m2) bloom_set(bt.tier[1], shard, a, b);
+    bloom_set(bt.tier[0], shard, a, b);
+  }
+};
+
+// giant steps: tier-1 probe; positives go to a candidate queue     (keyhunt.cpp:4819-4823)
+struct GiantCand {
+  uint64_t batch;
+  uint32_t idx;
+  uint32_t pad;
+};
+struct GiantSink {
+  GiantCand *cands;
+  uint32_t *count;
+  uint32_t cap;
+  uint32_t pad;
+  uint64_t n_steps;        // giant steps >= n_steps are outside the reference's walk and are skipped
+};
+struct GiantEmit {
+  static constexpr bool NEED_Y = false;
+  const BloomDev &tier1;
+  const GiantSink &sink;
+  KH_HDM GiantEmit(const BloomDev &b, const GiantSink &s) : tier1(b), sink(s) {}
+  KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
+    if (batch * KH_GRP + idx >= sink.n_steps) return;
+    uint32_t w[8];
+    fe_to_le_words(w, x);
+    const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);
+    const uint64_t b = xxh64_32(w, a);
+    if (bloom_test(tier1, x.v[7] >> 24, a, b)) {
+      uint32_t slot = kh_atomic_inc(sink.count);
+      if (slot < sink.cap) { GiantCand c; c.batch = batch; c.idx = idx; c.pad = 0; sink.cands[slot] = c; }
+    }
+  }
+};
+
+}  // namespace kh

@@ -1,0 +1,303 @@
+// fe.cuh — secp256k1 field arithmetic for sm_100a, 8 x 32-bit limbs in registers.
+//
+// Replaces the reference's 4x64-bit Int::ModMulK1 / ModSquareK1 / ModAdd / ModSub / ModNeg / ModInv
+// (secp256k1/IntMod.cpp:855, :977, :41, :72, :102, :382).  Values are ALWAYS canonical (< P) on
+// entry and exit, so serialised X/Y bytes equal the reference's Int::Get32Bytes output.
+//
+// Multiplication is operand-scanning schoolbook in the "even/odd column" arrangement: every
+// 32x32->64 product is one (mad.lo.cc, madc.hi.cc) pair that lands on two ADJACENT limbs of one
+// of two accumulators, so ptxas fuses the pair into a single IMAD.WIDE.U32(.X) on the FMA-heavy
+// pipe and the carry chain rides on the multiplies (64 IMAD.WIDE per 256x256 product instead of
+// 128 IMAD + 128 IMAD.HI).  Reduction folds the high 256 bits by 2^32+977 (P = 2^256-2^32-977).
+//
+// The limb-level primitives (kh_add8 / kh_sub8 / kh_mad_row) have a PTX carry-chain body for the
+// device and a portable body for the host; the host body exists ONLY so tests/devsim can unit-test
+// this exact limb algorithm on a machine without a GPU.  It is never part of the product path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KH_HD __host__ __device__ __forceinline__
+#define KH_HDM __host__ __device__ __forceinline__   // member functions
+#else
+#define KH_HD static inline
+#define KH_HDM inline
+#endif
+
+namespace kh {
+
+struct fe {
+  uint32_t v[8];  // little-endian limbs
+};
+
+// ---- limb primitives ---------------------------------------------------------------------------
+// r = a + b, returns carry (0/1)
+KH_HD uint32_t kh_add8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+  uint32_t cf;
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;\n\t"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cf)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + b[i]; r[i] = (uint32_t)c; c >>= 32; }
+  cf = (uint32_t)c;
+#endif
+  return cf;
+}
+// r = a - b, returns borrow mask (0xFFFFFFFF on borrow, else 0)
+KH_HD uint32_t kh_sub8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+  uint32_t m;
+#ifdef __CUDA_ARCH__
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(m)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)a[i] - b[i] - bw;
+    r[i] = (uint32_t)d;
+    bw = (d >> 32) & 1;
+  }
+  m = bw ? 0xFFFFFFFFu : 0u;
+#endif
+  return m;
+}
+// acc[0..7] += (a0,a2,a4,a6) * b as four adjacent 64-bit lanes; the carry-out is added into acc[8]
+KH_HD void kh_mad_row(uint32_t *acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "+r"(acc[8])
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+#else
+  const uint32_t a[4] = {a0, a2, a4, a6};
+  uint64_t c = 0;
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)a[k] * b;
+    uint64_t t = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)t;
+    c = t >> 32;
+    t = (uint64_t)acc[2 * k + 1] + (p >> 32) + c;
+    acc[2 * k + 1] = (uint32_t)t;
+    c = t >> 32;
+  }
+  acc[8] += (uint32_t)c;
+#endif
+}
+// r[0..15] = e[0..15] + (o[0..14] << 32)   (final combination of the even/odd accumulators)
+KH_HD void kh_combine_eo(uint32_t r[16], const uint32_t e[17], const uint32_t o[17]) {
+  r[0] = e[0];
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;\n\t"
+      : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]),
+        "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
+      : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+        "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]),
+        "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+        "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]));
+#else
+  uint64_t c = 0;
+  for (int i = 1; i < 16; i++) { c += (uint64_t)e[i] + o[i - 1]; r[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
+KH_HD uint32_t kh_umulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// ---- basic helpers -------------------------------------------------------------------------------
+KH_HD void fe_set_zero(fe &r) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+KH_HD void fe_set_u32(fe &r, uint32_t x) {
+  fe_set_zero(r);
+  r.v[0] = x;
+}
+KH_HD bool fe_is_zero(const fe &a) {
+  return (a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) == 0;
+}
+KH_HD bool fe_eq(const fe &a, const fe &b) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d |= a.v[i] ^ b.v[i];
+  return d == 0;
+}
+
+// ---- add / sub / neg (mod P, canonical) ----------------------------------------------------------
+// P = 2^256 - C, C = 2^32 + 977
+KH_HD void fe_sub(fe &r, const fe &a, const fe &b) {
+  uint32_t t[8];
+  uint32_t m = kh_sub8(t, a.v, b.v);
+  const uint32_t c[8] = {m & 977u, m & 1u, 0, 0, 0, 0, 0, 0};  // on borrow: + P  ==  - C (mod 2^256)
+  kh_sub8(r.v, t, c);
+}
+// value = t + cf*2^256 (known < 2P)  ->  r = value mod P
+KH_HD void fe_final_reduce(fe &r, const uint32_t t[8], uint32_t cf) {
+  const uint32_t c[8] = {977u, 1u, 0, 0, 0, 0, 0, 0};
+  uint32_t u[8];
+  uint32_t k = kh_add8(u, t, c);
+  bool take = (cf | k) != 0;  // value >= P  <=>  value + C >= 2^256
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = take ? u[i] : t[i];
+}
+KH_HD void fe_add(fe &r, const fe &a, const fe &b) {
+  uint32_t t[8];
+  uint32_t cf = kh_add8(t, a.v, b.v);
+  fe_final_reduce(r, t, cf);
+}
+KH_HD void fe_neg(fe &r, const fe &a) {  // 0 -> 0
+  fe z;
+  fe_set_zero(z);
+  fe_sub(r, z, a);
+}
+
+// ---- 256 x 256 -> 512 ------------------------------------------------------------------------------
+KH_HD void fe_mul_wide(uint32_t r[16], const fe &a, const fe &b) {
+  // e[k] <-> column k ; o[k] <-> column k+1
+  uint32_t e[17], o[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    // row i (even): even j -> even column -> e[i+j] ; odd j -> odd column -> o[i+j-1]
+    kh_mad_row(e + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+    kh_mad_row(o + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    // row i+1 (odd): odd j -> even column -> e[i+1+j] ; even j -> odd column -> o[i+j]
+    kh_mad_row(e + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+    kh_mad_row(o + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+  }
+  kh_combine_eo(r, e, o);
+}
+
+// ---- 512 -> 256 (mod P), canonical ------------------------------------------------------------------
+KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
+  // t = lo + hi*977 + (hi << 32), 10 limbs
+  uint32_t e[9], o[9];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { e[i] = w[i]; o[i] = 0; }
+  e[8] = 0; o[8] = 0;
+  kh_mad_row(e, w[8], w[10], w[12], w[14], 977u);  // hi limbs 0,2,4,6 -> columns 0,2,4,6
+  kh_mad_row(o, w[9], w[11], w[13], w[15], 977u);  // hi limbs 1,3,5,7 -> columns 1,3,5,7 (o[k] <-> limb k+1)
+  uint32_t t[8], top0, top1;
+  // limbs 1..8 : e[1..8] + o[0..7] ; limb 9 : o[8] + carry
+  uint32_t s[8];
+  uint32_t cf = kh_add8(s, e + 1, o);
+  top1 = o[8] + cf;
+  // += hi << 32 (limbs 1..8)
+  cf = kh_add8(s, s, w + 8);
+  top1 += cf;
+  t[0] = e[0];
+#pragma unroll
+  for (int i = 0; i < 7; i++) t[1 + i] = s[i];
+  top0 = s[7];
+  // second fold: top = top0 + top1*2^32 (< 2^35): t += top*977 + (top << 32)
+  const uint32_t f1[8] = {top0 * 977u, kh_umulhi(top0, 977u) + top1 * 977u, top1, 0, 0, 0, 0, 0};
+  const uint32_t f2[8] = {0, top0, 0, 0, 0, 0, 0, 0};
+  uint32_t cfa = kh_add8(t, t, f1);
+  uint32_t cfb = kh_add8(t, t, f2);
+  fe_final_reduce(r, t, cfa | cfb);
+}
+
+KH_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+  uint32_t w[16];
+  fe_mul_wide(w, a, b);
+  fe_reduce_wide(r, w);
+}
+KH_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+
+// r = a^(2^n)
+KH_HD void fe_sqr_n(fe &r, const fe &a, int n) {
+  r = a;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) fe_sqr(r, r);
+}
+
+// a^(P-2): 255 squarings + 15 multiplications (addition chain over the run-lengths of P-2:
+// 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1).  inv(0) = 0, like Int::ModInv's "no inverse" result.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+void fe_inv(fe &r, const fe &a) {
+  fe x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223, t;
+  fe_sqr(x2, a); fe_mul(x2, x2, a);
+  fe_sqr(x3, x2); fe_mul(x3, x3, a);
+  fe_sqr_n(x6, x3, 3); fe_mul(x6, x6, x3);
+  fe_sqr_n(x9, x6, 3); fe_mul(x9, x9, x3);
+  fe_sqr_n(x11, x9, 2); fe_mul(x11, x11, x2);
+  fe_sqr_n(x22, x11, 11); fe_mul(x22, x22, x11);
+  fe_sqr_n(x44, x22, 22); fe_mul(x44, x44, x22);
+  fe_sqr_n(x88, x44, 44); fe_mul(x88, x88, x44);
+  fe_sqr_n(x176, x88, 88); fe_mul(x176, x176, x88);
+  fe_sqr_n(x220, x176, 44); fe_mul(x220, x220, x44);
+  fe_sqr_n(x223, x220, 3); fe_mul(x223, x223, x3);
+  fe_sqr_n(t, x223, 23); fe_mul(t, t, x22);
+  fe_sqr_n(t, t, 5); fe_mul(t, t, a);
+  fe_sqr_n(t, t, 3); fe_mul(t, t, x2);
+  fe_sqr_n(t, t, 2); fe_mul(r, t, a);
+}
+
+// ---- (de)serialisation -------------------------------------------------------------------------------
+// 32-byte big-endian string (Int::Get32Bytes, Int.cpp:308) <-> limbs
+KH_HD void fe_from_be(fe &r, const uint8_t *b) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t *p = b + 4 * (7 - i);
+    r.v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+  }
+}
+KH_HD void fe_to_be(uint8_t *b, const fe &a) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t *p = b + 4 * (7 - i);
+    p[0] = (uint8_t)(a.v[i] >> 24); p[1] = (uint8_t)(a.v[i] >> 16); p[2] = (uint8_t)(a.v[i] >> 8); p[3] = (uint8_t)a.v[i];
+  }
+}
+
+}  // namespace kh

@@ -1,0 +1,139 @@
+// tests/devsim/devsim.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's device headers (keyhunt_b200/csrc/*.cuh) for the HOST with plain g++ so the
+// limb algorithms, message packers, batch geometry, bloom arithmetic and emit logic can be unit
+// tested against the oracle on a machine that has no GPU (`pytest -m "not gpu"`).  The PTX bodies are
+// replaced by the portable bodies that sit beside them in the same functions; everything else is
+// the very code the kernels run.  This library is never loaded by keyhunt_b200 and is not a fallback:
+// the product path requires libkh_b200.so + a GPU.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../keyhunt_b200/csrc/emit.cuh"
+#include "../../keyhunt_b200/csrc/setup.cuh"
+
+using namespace kh;
+
+extern "C" {
+
+void ds_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_mul(r, x, y); fe_to_be(out, r); }
+void ds_fe_sqr(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_sqr(r, x); fe_to_be(out, r); }
+void ds_fe_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_add(r, x, y); fe_to_be(out, r); }
+void ds_fe_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_sub(r, x, y); fe_to_be(out, r); }
+void ds_fe_inv(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_inv(r, x); fe_to_be(out, r); }
+
+void ds_pubkey(const uint8_t key[32], uint8_t xy[64]) {
+  u256 k; u256_from_be(k, key);
+  ge p; ge_mul_g(p, k);
+  fe_to_be(xy, p.x); fe_to_be(xy + 32, p.y);
+}
+static void words_to_bytes(uint8_t out[20], const uint32_t w[5]) {
+  for (int i = 0; i < 5; i++) { out[4 * i] = (uint8_t)w[i]; out[4 * i + 1] = (uint8_t)(w[i] >> 8); out[4 * i + 2] = (uint8_t)(w[i] >> 16); out[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+}
+void ds_hash160_comp(int prefix, const uint8_t x[32], uint8_t out[20]) { fe v; fe_from_be(v, x); uint32_t h[5]; hash160_compressed(h, (uint32_t)prefix, v); words_to_bytes(out, h); }
+void ds_hash160_uncomp(const uint8_t xy[64], uint8_t out[20]) { fe x, y; fe_from_be(x, xy); fe_from_be(y, xy + 32); uint32_t h[5]; hash160_uncompressed(h, x, y); words_to_bytes(out, h); }
+void ds_eth_addr(const uint8_t xy[64], uint8_t out[20]) { fe x, y; fe_from_be(x, xy); fe_from_be(y, xy + 32); uint32_t h[5]; eth_address(h, x, y); words_to_bytes(out, h); }
+uint64_t ds_xxh64_20(const uint8_t b[20], uint64_t seed) { uint32_t w[5]; memcpy(w, b, 20); return xxh64_20(w, seed); }
+uint64_t ds_xxh64_32(const uint8_t b[32], uint64_t seed) { uint32_t w[8]; memcpy(w, b, 32); return xxh64_32(w, seed); }
+uint64_t ds_bloom_mod(uint64_t x, uint64_t bits) { return bloom_mod(x, bits, (~0ULL) / bits); }
+
+// ---- scan emulation: what the host API + kernels do, with T walker "threads" run one after another ----
+struct DsHit { uint64_t index; uint32_t kind; uint8_t matched[20]; uint32_t pad; };
+
+static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vector<uint32_t> &centers, std::vector<kh_u4> &scratch) {
+  gtab.resize(KH_TAB_WORDS);
+  for (uint32_t e = 0; e < KH_TAB_ENTRIES; e++) setup_table_entry(&gtab[16 * e], ws, e);
+  centers.resize(16 * ws.T);
+  for (uint64_t t = 0; t < ws.T; t++) {
+    fe cx, cy;
+    setup_center(cx, cy, ws, t);
+    for (int l = 0; l < 8; l++) { centers[l * ws.T + t] = cx.v[l]; centers[(8 + l) * ws.T + t] = cy.v[l]; }
+  }
+  scratch.resize((size_t)1024 * ws.T);
+}
+
+// kind: KH_SCAN_*; table20: N sorted 20-byte records; bloom image as bytes
+int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint8_t *bloom_bytes, uint64_t bloom_bits,
+                uint32_t bloom_hashes, const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T,
+                uint32_t steps_per_launch, DsHit *out, uint32_t max_hits) {
+  WalkSetup ws;
+  memset(&ws, 0, sizeof(ws));
+  u256_from_be(ws.s, stride);
+  u256_from_be(ws.k0, start);
+  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
+  std::vector<uint32_t> gtab, centers;
+  std::vector<kh_u4> scratch;
+  make_walk(ws, gtab, centers, scratch);
+
+  std::vector<uint32_t> table(5 * n_targets);
+  for (uint64_t i = 0; i < n_targets; i++)
+    for (int k = 0; k < 5; k++) {
+      const uint8_t *p = table20 + 20 * i + 4 * k;
+      table[5 * i + k] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+    }
+  std::vector<RawHit> raw(max_hits);
+  uint32_t count = 0;
+  ScanTargets tg;
+  tg.bloom.bf = const_cast<uint8_t *>(bloom_bytes);
+  tg.bloom.bits = bloom_bits; tg.bloom.magic = (~0ULL) / bloom_bits; tg.bloom.stride = 0; tg.bloom.hashes = bloom_hashes;
+  tg.table = table.data(); tg.n = n_targets;
+  tg.sink.hits = raw.data(); tg.sink.count = &count; tg.sink.cap = max_hits;
+
+  WalkParams wp;
+  wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
+  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch;
+  for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
+    wp.batch_base = base;
+    for (uint64_t t = 0; t < T; t++) {
+      switch (kind) {
+        case KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        default: return -1;
+      }
+    }
+  }
+  uint32_t n = count < max_hits ? count : max_hits;
+  for (uint32_t i = 0; i < n; i++) {
+    out[i].index = raw[i].batch * KH_GRP + raw[i].idx;
+    out[i].kind = raw[i].kind;
+    words_to_bytes(out[i].matched, raw[i].h);
+    out[i].pad = 0;
+  }
+  return count;
+}
+
+// all X (and Y) of the first n_batches batches, in range order: out[(b*1024+i)*64]
+struct DumpEmit {
+  static constexpr bool NEED_Y = true;
+  uint8_t *out;
+  void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
+    uint8_t *p = out + (batch * KH_GRP + idx) * 64;
+    fe_to_be(p, x); fe_to_be(p + 32, y);
+  }
+};
+void ds_walk_dump(const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T, uint32_t steps_per_launch, uint8_t *out) {
+  WalkSetup ws;
+  memset(&ws, 0, sizeof(ws));
+  u256_from_be(ws.s, stride);
+  u256_from_be(ws.k0, start);
+  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
+  std::vector<uint32_t> gtab, centers;
+  std::vector<kh_u4> scratch;
+  make_walk(ws, gtab, centers, scratch);
+  WalkParams wp;
+  wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
+  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch;
+  DumpEmit e; e.out = out;
+  for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
+    wp.batch_base = base;
+    for (uint64_t t = 0; t < T; t++) walk_batches(wp, gtab.data(), t, e);
+  }
+}
+
+}  // extern "C"

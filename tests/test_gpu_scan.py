@@ -1,0 +1,117 @@
+"""GPU parity tests for the scan path: every call goes through the C ABI (libkh_b200.so) and is compared
+bit-for-bit with the CPU oracle on the same seeded inputs."""
+import os
+import random
+
+import pytest
+
+import keyhunt_b200 as K
+from _oracle import (CRYPTO_BTC as O_BTC, CRYPTO_ETH as O_ETH, MODE_ADDRESS as O_ADDR, MODE_RMD160 as O_RMD,
+                     MODE_XPOINT as O_XP, N_ORDER, SEARCH_BOTH, SEARCH_COMPRESS, SEARCH_UNCOMPRESS, be32)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_derive_matches_oracle(kh, oracle):
+    rnd = random.Random(11)
+    keys = [1, 2, 3, 7, 0xFFFFFFFF, 2**64 + 5, N_ORDER - 1, N_ORDER - 2] + [rnd.randrange(1, N_ORDER) for _ in range(300)]
+    infos = kh.derive(keys)
+    for k, info in zip(keys, infos):
+        x, y = oracle.pubkey(k)
+        assert (info.pub_x, info.pub_y) == (x, y), hex(k)
+        assert info.h160_comp == oracle.hash160_comp(2 + (y & 1), x)
+        assert info.h160_uncomp == oracle.hash160_uncomp(x, y)
+        assert info.eth == oracle.eth_addr(x, y)
+
+
+def _hits_set(hits):
+    return sorted((h.index, h.kind, h.key, h.matched) for h in hits)
+
+
+def _ohits_set(hits):
+    return sorted((h["index"], h["kind"], h["key"], h["matched"]) for h in hits)
+
+
+def _planted(oracle, rnd, start, stride, n_points, kind, count):
+    """targets planted inside the range for every hit kind + random decoys"""
+    recs, idxs = [], sorted(set([0, 1, 511, 512, 513, 1023, 1024, n_points - 1] + [rnd.randrange(n_points) for _ in range(count)]))
+    for j, i in enumerate(idxs):
+        x, y = oracle.pubkey((start + i * stride) % N_ORDER)
+        if kind == "xpoint":
+            recs.append(be32(x)[:20])
+        elif kind == "eth":
+            recs.append(oracle.eth_addr(x, y))
+        elif kind == "comp":
+            # mix: real prefix, and the opposite prefix (a target whose key is n-k)
+            pre = 2 + (y & 1)
+            recs.append(oracle.hash160_comp(pre if j % 3 else 5 - pre, x))
+        elif kind == "uncomp":
+            recs.append(oracle.hash160_uncomp(x, y))
+        else:  # both
+            recs.append(oracle.hash160_uncomp(x, y) if j % 2 else oracle.hash160_comp(2 + (y & 1), x))
+    recs += [rnd.randbytes(20) for _ in range(200)]
+    rnd.shuffle(recs)
+    return b"".join(recs)
+
+
+CASES = [
+    ("xpoint", K.MODE_XPOINT, K.CRYPTO_BTC, K.SEARCH_COMPRESS, O_XP, O_BTC, SEARCH_COMPRESS),
+    ("comp", K.MODE_RMD160, K.CRYPTO_BTC, K.SEARCH_COMPRESS, O_RMD, O_BTC, SEARCH_COMPRESS),
+    ("uncomp", K.MODE_RMD160, K.CRYPTO_BTC, K.SEARCH_UNCOMPRESS, O_RMD, O_BTC, SEARCH_UNCOMPRESS),
+    ("both", K.MODE_ADDRESS, K.CRYPTO_BTC, K.SEARCH_BOTH, O_ADDR, O_BTC, SEARCH_BOTH),
+    ("eth", K.MODE_ADDRESS, K.CRYPTO_ETH, K.SEARCH_COMPRESS, O_ADDR, O_ETH, SEARCH_COMPRESS),
+]
+
+
+@pytest.mark.parametrize("name,mode,crypto,search,omode,ocrypto,osearch", CASES)
+@pytest.mark.parametrize("start,stride,n_points", [(1, 1, 1 << 16), (0x2000000000000000, 1, 3 * 1024),
+                                                   (0xDEADBEEF12345, 977, 1 << 14)])
+def test_scan_matches_oracle(kh, oracle, name, mode, crypto, search, omode, ocrypto, osearch, start, stride, n_points):
+    rnd = random.Random(hash((name, start, stride)) & 0xFFFF)
+    recs = _planted(oracle, rnd, start, stride, n_points, name, 12)
+    kh.set_targets(mode, recs, crypto=crypto, search=search)
+    # device-built bloom image and sorted table equal the oracle's (bloom_add / _sort parity)
+    t = oracle.targets_new(recs)
+    desc, bits = kh.get_bloom()
+    assert desc.as_dict() == oracle.bloom_desc(oracle.targets_bloom(t))
+    assert bits == oracle.bloom_bytes(oracle.targets_bloom(t))
+    assert kh.get_table() == oracle.targets_table(t)
+    kh.scan(start, n_points, stride)
+    got = kh.poll_hits()
+    want = oracle.scan(t, omode, ocrypto, osearch, start, stride, n_points)
+    oracle.targets_free(t)
+    assert len(want) >= 8
+    assert _hits_set(got) == _ohits_set(want)
+    for h in got:  # reported key really owns the reported public key
+        assert oracle.pubkey(h.key) == (h.pub_x, h.pub_y)
+
+
+def test_golden_puzzles_1_to_32_first_2pow24(kh):
+    """reference fixture tests/1to32.rmd; hit list pinned by the unmodified reference binary
+    (`keyhunt -m rmd160 -f tests/1to32.rmd -r 1:FFFFFF -l compress`, see tests/golden/README.md)"""
+    recs = K.parse_targets(open(os.path.join(GOLD, "1to32.rmd")), K.MODE_RMD160)
+    assert len(recs) == 32 * 20
+    kh.set_targets(K.MODE_RMD160, recs, search=K.SEARCH_COMPRESS)
+    kh.scan(1, 1 << 24)
+    keys = sorted(h.key for h in kh.poll_hits())
+    assert keys == [0x1, 0x3, 0x7, 0x8, 0x15, 0x31, 0x4c, 0xe0, 0x1d3, 0x202, 0x483, 0xa7b, 0x1460, 0x2930, 0x68f3,
+                    0xc936, 0x1764f, 0x3080d, 0x5749f, 0xd2c55, 0x1ba534, 0x2de40f, 0x556e52, 0xdc2a04]
+
+
+def test_multi_launch_and_tail(kh, oracle):
+    """range that needs several launches per thread and ends mid-wave"""
+    kh.set_option("steps_per_launch", 2)
+    kh.set_option("threads_per_sm", 64)
+    try:
+        rnd = random.Random(5)
+        start, n_points = 0x7000000000000123, 1024 * 40000 + 1024 * 7
+        idxs = [0, n_points - 1, n_points // 2] + [rnd.randrange(n_points) for _ in range(20)]
+        recs = b"".join(be32(oracle.pubkey(start + i)[0])[:20] for i in idxs)
+        kh.set_targets(K.MODE_XPOINT, recs)
+        kh.scan(start, n_points)
+        got = sorted(h.index for h in kh.poll_hits())
+        assert got == sorted(set(idxs))
+    finally:
+        kh.set_option("steps_per_launch", 16)
+        kh.set_option("threads_per_sm", 512)
