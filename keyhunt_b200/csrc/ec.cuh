@@ -185,9 +185,8 @@ KH_HD void ge_add_direct(ge &r, const ge &p1, const ge &p2) {
 }
 // r = a + b, r = a - b for a small b (keys near a base key)
 KH_HD void u256_add_u64(u256 &r, const u256 &a, uint64_t b) {
-  uint64_t c = b;
-#pragma unroll
-  for (int i = 0; i < 8; i++) { c += a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; if (i == 0) c += 0; }
+  uint32_t bb[8] = {(uint32_t)b, (uint32_t)(b >> 32), 0, 0, 0, 0, 0, 0};
+  kh_add8(r.v, a.v, bb);
 }
 KH_HD void u256_sub_u64(u256 &r, const u256 &a, uint64_t b) {
   uint32_t bb[8] = {(uint32_t)b, (uint32_t)(b >> 32), 0, 0, 0, 0, 0, 0};

@@ -141,7 +141,8 @@ struct GiantCand {
   uint32_t idx;
   uint32_t pad;
 };
-struct GiantSink {
+struct GiantParams {
+  BloomDev tier1;
   GiantCand *cands;
   uint32_t *count;
   uint32_t cap;
@@ -150,18 +151,17 @@ struct GiantSink {
 };
 struct GiantEmit {
   static constexpr bool NEED_Y = false;
-  const BloomDev &tier1;
-  const GiantSink &sink;
-  KH_HDM GiantEmit(const BloomDev &b, const GiantSink &s) : tier1(b), sink(s) {}
+  const GiantParams &gp;
+  KH_HDM explicit GiantEmit(const GiantParams &g) : gp(g) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
-    if (batch * KH_GRP + idx >= sink.n_steps) return;
+    if (batch * KH_GRP + idx >= gp.n_steps) return;
     uint32_t w[8];
     fe_to_le_words(w, x);
     const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);
     const uint64_t b = xxh64_32(w, a);
-    if (bloom_test(tier1, x.v[7] >> 24, a, b)) {
-      uint32_t slot = kh_atomic_inc(sink.count);
-      if (slot < sink.cap) { GiantCand c; c.batch = batch; c.idx = idx; c.pad = 0; sink.cands[slot] = c; }
+    if (bloom_test(gp.tier1, x.v[7] >> 24, a, b)) {
+      uint32_t slot = kh_atomic_inc(gp.count);
+      if (slot < gp.cap) { GiantCand c; c.batch = batch; c.idx = idx; c.pad = 0; gp.cands[slot] = c; }
     }
   }
 };

@@ -1,10 +1,455 @@
-// kh_bsgs.cu — BSGS half of the C ABI (placeholder until the kernels land in the next commit).
+// kh_bsgs.cu — BSGS half of the C ABI: baby-step table + 3-tier bloom build, giant-step walk, tier-2/3
+// refinement, all resident in HBM (no host round trip between a tier-1 positive and the verified key).
+//
+// Kernels:
+//   kh_baby_kernel    walk of (i+1)*G, i < m: atomicOr into the 3 x 256 bloom shards + bP table fill
+//                     (thread_bPload keyhunt.cpp:5284-5472)
+//   kh_bitonic_step   sorts the bP table by (6-byte key, index)     (bsgs_sort keyhunt.cpp:4412)
+//   kh_giant_kernel   walk of Q - (base + (2g+1)m)G with the tier-1 probe fused in
+//                     (thread_process_bsgs keyhunt.cpp:4644-4823)
+//   kh_refine_kernel  one warp per tier-1 positive: lanes = the 32 tier-2 sub-steps, then the 32
+//                     tier-3 sub-steps, bP lookup and key verification
+//                     (bsgs_secondcheck :5151, bsgs_thirdcheck :5186, bsgs_searchbinary :4510)
+//   kh_amp_kernel     BSGS_AMP2 / BSGS_AMP3 tables (keyhunt.cpp:1818-1842)
+#include <algorithm>
+
 #include "kh_ctx.cuh"
 
-extern "C" {
-int kh_bsgs_build(kh_ctx *c, uint64_t, uint32_t) { return kh_fail(c, KH_ESTATE, "bsgs not built yet"); }
-int kh_bsgs_describe(kh_ctx *c, kh_bsgs_desc *) { return kh_fail(c, KH_ESTATE, "bsgs not built yet"); }
-int kh_bsgs_export(kh_ctx *c, int, int, void *, uint64_t) { return kh_fail(c, KH_ESTATE, "bsgs not built yet"); }
-int kh_bsgs_import(kh_ctx *c, int, int, const void *, uint64_t) { return kh_fail(c, KH_ESTATE, "bsgs not built yet"); }
-int kh_bsgs_search(kh_ctx *c, const uint8_t *, const uint8_t *, const uint8_t *, uint8_t *, int *) { return kh_fail(c, KH_ESTATE, "bsgs not built yet"); }
+using namespace kh;
+
+#define KH_BLOCK 256
+
+__device__ __forceinline__ void kh_stage_table_b(uint32_t *smem, const uint32_t *gtab) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
+  uint4 *dst = reinterpret_cast<uint4 *>(smem);
+  for (int i = threadIdx.x; i < KH_TAB_WORDS / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
 }
+
+__global__ void __launch_bounds__(KH_BLOCK, 2) kh_baby_kernel(WalkParams wp, BsgsTables bt) {
+  extern __shared__ __align__(16) uint32_t kh_smem_tab[];
+  kh_stage_table_b(kh_smem_tab, wp.gtab);
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wp.T) return;
+  BabyEmit emit(bt);
+  walk_batches(wp, kh_smem_tab, t, emit);
+}
+
+__global__ void __launch_bounds__(KH_BLOCK, 2) kh_giant_kernel(WalkParams wp, GiantParams gp) {
+  extern __shared__ __align__(16) uint32_t kh_smem_tab[];
+  kh_stage_table_b(kh_smem_tab, wp.gtab);
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wp.T) return;
+  GiantEmit emit(gp);
+  walk_batches(wp, kh_smem_tab, t, emit);
+}
+
+// ---- bP table sort -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t bp_key48(const BpEntry &e) {
+  return ((uint64_t)e.value[0] << 40) | ((uint64_t)e.value[1] << 32) | ((uint64_t)e.value[2] << 24) |
+         ((uint64_t)e.value[3] << 16) | ((uint64_t)e.value[4] << 8) | (uint64_t)e.value[5];
+}
+__global__ void kh_bp_pad(BpEntry *tab, uint64_t m3, uint64_t n2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + m3;
+  if (i >= n2) return;
+  BpEntry e;
+  for (int k = 0; k < 6; k++) e.value[k] = 0xFF;
+  e.pad[0] = e.pad[1] = 0;
+  e.index = ~0ULL;   // sentinels sort after every real entry
+  tab[i] = e;
+}
+__global__ void kh_bitonic_step(BpEntry *tab, uint64_t n2, uint64_t j, uint64_t k) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const uint64_t ixj = i ^ j;
+  if (ixj <= i) return;
+  BpEntry a = tab[i], b = tab[ixj];
+  const uint64_t ka = bp_key48(a), kb = bp_key48(b);
+  const bool a_gt_b = (ka != kb) ? (ka > kb) : (a.index > b.index);
+  const bool ascending = (i & k) == 0;
+  if (a_gt_b == ascending) { tab[i] = b; tab[ixj] = a; }
+}
+
+// ---- AMP tables: entry i (<32) = -(2i+1)*m2*G, entry 32+i = -(2i+1)*m3*G ------------------------------
+__global__ void __launch_bounds__(64) kh_amp_kernel(uint32_t *aux, uint64_t m2, uint64_t m3) {
+  const uint32_t i = threadIdx.x;
+  if (i >= 64) return;
+  u256 k, z, mm;
+  u256_set_u64(z, 0);
+  u256_set_u64(mm, i < 32 ? m2 : m3);
+  u256_add_mul64(k, z, mm, 2ull * (i & 31) + 1ull);
+  ge p;
+  ge_mul_g(p, k);
+  ge_neg(p, p);
+#pragma unroll
+  for (int l = 0; l < 8; l++) { aux[16 * i + l] = p.x.v[l]; aux[16 * i + 8 + l] = p.y.v[l]; }
+}
+
+// ---- refinement ---------------------------------------------------------------------------------------
+struct RefineParams {
+  BsgsTables bt;
+  const uint32_t *aux;      // AMP2 | AMP3
+  const GiantCand *cands;
+  uint32_t n_cands;
+  uint32_t pad;
+  ge q;                     // target public key
+  u256 start;               // range start (base key of window 0)
+  uint32_t *found;          // [0] flag
+  u256 *found_key;
+};
+
+__device__ __forceinline__ void load_aux_point(ge &p, const uint32_t *aux, int i) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) { p.x.v[l] = aux[16 * i + l]; p.y.v[l] = aux[16 * i + 8 + l]; }
+  p.inf = 0;
+}
+__device__ __forceinline__ bool tier_check(const BloomDev &bl, const fe &x) {
+  uint32_t w[8];
+  fe_to_le_words(w, x);
+  const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);
+  const uint64_t b = xxh64_32(w, a);
+  return bloom_test(bl, x.v[7] >> 24, a, b);
+}
+// S = Q - key*G  (AddDirect(Q, Negation(ComputePublicKey(key))), keyhunt.cpp:5163-5171)
+__device__ __noinline__ void q_minus_key(ge &s, const ge &q, const u256 &key) {
+  ge bp;
+  ge_mul_g(bp, key);
+  ge_neg(bp, bp);
+  ge_add_direct(s, q, bp);
+}
+__device__ __noinline__ bool key_matches(const ge &q, const u256 &key) {
+  ge p;
+  ge_mul_g(p, key);
+  return !p.inf && fe_eq(p.x, q.x);
+}
+
+__global__ void __launch_bounds__(32) kh_refine_kernel(RefineParams rp) {
+  const uint32_t cand = blockIdx.x;
+  if (cand >= rp.n_cands) return;
+  const uint32_t lane = threadIdx.x;
+  const GiantCand c = rp.cands[cand];
+  const uint64_t g = c.batch * KH_GRP + c.idx;            // global giant-step number (window*aux + a)
+  // base2 = start + g*2m   (bsgs_secondcheck keyhunt.cpp:5159-5161, windows being contiguous)
+  u256 two_m, base2;
+  u256_set_u64(two_m, rp.bt.m);
+  { u256 z; u256_set_u64(z, 0); u256_add_mul64(two_m, z, two_m, 2); }
+  u256_add_mul64(base2, rp.start, two_m, g);
+  ge S;
+  q_minus_key(S, rp.q, base2);
+  // tier 2: lane i2 tests S + AMP2[i2]
+  ge amp, P2;
+  load_aux_point(amp, rp.aux, (int)lane);
+  ge_add_direct(P2, S, amp);
+  const bool pos2 = tier_check(rp.bt.tier[1], P2.x);
+  uint32_t mask2 = __ballot_sync(0xFFFFFFFFu, pos2);
+  while (mask2) {
+    const uint32_t i2 = __ffs(mask2) - 1;
+    mask2 &= mask2 - 1;
+    // base3 = base2 + i2*2*m2   (bsgs_thirdcheck keyhunt.cpp:5194-5196)
+    u256 two_m2, base3;
+    u256_set_u64(two_m2, rp.bt.m2);
+    { u256 z; u256_set_u64(z, 0); u256_add_mul64(two_m2, z, two_m2, 2); }
+    u256_add_mul64(base3, base2, two_m2, (uint64_t)i2);
+    ge S3, P3;
+    q_minus_key(S3, rp.q, base3);
+    load_aux_point(amp, rp.aux, 32 + (int)lane);
+    ge_add_direct(P3, S3, amp);
+    // calcualteindex(i3) = (2*i3+1)*m3   (keyhunt.cpp:7859)
+    u256 calc, m3v, key;
+    u256_set_u64(m3v, rp.bt.m3);
+    { u256 z; u256_set_u64(z, 0); u256_add_mul64(calc, z, m3v, 2ull * lane + 1ull); }
+    bool ok = false;
+    if (tier_check(rp.bt.tier[2], P3.x)) {
+      // bsgs_searchbinary on X bytes 16..21; every entry sharing the 6-byte key is tried
+      const uint64_t want = ((uint64_t)P3.x.v[3] << 16) | (P3.x.v[2] >> 16);
+      uint64_t lo = 0, hi = rp.bt.m3;
+      while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (bp_key48(rp.bt.table[mid]) < want) lo = mid + 1; else hi = mid;
+      }
+      while (!ok && lo < rp.bt.m3 && bp_key48(rp.bt.table[lo]) == want) {
+        const uint64_t j1 = rp.bt.table[lo].index + 1;
+        u256 t;
+        u256_add_mul64(t, base3, calc, 1);
+        u256_add_u64(key, t, j1);                                   // keyhunt.cpp:5212-5219
+        if (key_matches(rp.q, key)) ok = true;
+        else { u256_sub_u64(key, t, j1); if (key_matches(rp.q, key)) ok = true; }   // :5221-5228
+        lo++;
+      }
+    } else if (fe_eq(S3.x, amp.x)) {                                // keyhunt.cpp:5238-5243
+      u256_add_mul64(key, base3, calc, 1);
+      ok = true;
+    }
+    const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, ok);
+    if (okmask) {
+      if (lane == (uint32_t)(__ffs(okmask) - 1)) {
+        if (atomicCAS(rp.found, 0u, 1u) == 0u) *rp.found_key = key;
+      }
+      return;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int ilog2_exact(uint64_t n) {
+  int lg = 0;
+  while (lg < 63 && (1ULL << lg) < n) lg++;
+  return ((1ULL << lg) == n) ? lg : -1;
+}
+static void free_bsgs(kh_ctx *c) {
+  for (int t = 0; t < 3; t++) { if (c->d_tier[t]) cudaFree(c->d_tier[t]); c->d_tier[t] = nullptr; }
+  if (c->d_bptable) cudaFree(c->d_bptable);
+  if (c->d_aux_tab) cudaFree(c->d_aux_tab);
+  c->d_bptable = nullptr; c->d_aux_tab = nullptr;
+  c->have_bsgs = false;
+}
+static void fill_tables(kh_ctx *c, BsgsTables &bt) {
+  for (int t = 0; t < 3; t++) {
+    bt.tier[t].bf = c->d_tier[t];
+    bt.tier[t].bits = c->bsgs.tier[t].bits;
+    bt.tier[t].magic = (~0ULL) / c->bsgs.tier[t].bits;
+    bt.tier[t].stride = c->tier_stride[t];
+    bt.tier[t].hashes = c->bsgs.tier[t].hashes;
+    bt.tier[t].pad = 0;
+  }
+  bt.table = c->d_bptable;
+  bt.m = c->bsgs.m; bt.m2 = c->bsgs.m2; bt.m3 = c->bsgs.m3;
+}
+
+extern "C" {
+
+int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
+  if (!c) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  // -n must have an exact square root (keyhunt.cpp:1474) that is a multiple of 1024 (:1509)
+  const int lg = ilog2_exact(n);
+  if (lg < 20 || (lg & 1) || k < 1) return kh_fail(c, KH_EINVAL, "bsgs n must be 2^even >= 2^20 and k >= 1");
+  free_bsgs(c);
+  kh_bsgs_desc d;
+  memset(&d, 0, sizeof(d));
+  d.m = (1ULL << (lg / 2)) * (uint64_t)k;                               // keyhunt.cpp:1557
+  d.m2 = d.m / 32 + ((d.m % 32) ? 1 : 0);                                // :1561-1566
+  d.m3 = d.m2 / 32 + ((d.m2 % 32) ? 1 : 0);                              // :1578-1583
+  d.aux = n / d.m;                                                       // :1591-1603
+  if (d.aux == 0) return kh_fail(c, KH_EINVAL, "k too large for n");
+  d.n = (n % d.m) ? d.m * d.aux : n;
+  const uint64_t items[3] = {
+      (d.m / 256 > 10000) ? (d.m / 256 + ((d.m % 256) ? 1 : 0)) : 1000,  // :1633-1661
+      (d.m2 / 256 > 1000) ? (d.m2 / 256 + ((d.m2 % 256) ? 1 : 0)) : 1000,
+      (d.m3 / 256 > 1000) ? (d.m3 / 256 + ((d.m3 % 256) ? 1 : 0)) : 1000};
+  for (int t = 0; t < 3; t++)
+    if (kh_bloom_params(items[t] <= 10000 ? 10000 : items[t], &d.tier[t]) != KH_OK) return kh_fail(c, KH_EINVAL, "bloom sizing");
+  c->bsgs = d;
+  for (int t = 0; t < 3; t++) {
+    c->tier_stride[t] = ((d.tier[t].bytes + 15) / 16) * 16;
+    KH_CUDA(c, cudaMalloc(&c->d_tier[t], (size_t)c->tier_stride[t] * 256));
+    KH_CUDA(c, cudaMemsetAsync(c->d_tier[t], 0, (size_t)c->tier_stride[t] * 256, c->stream));
+  }
+  uint64_t n2 = 1;
+  while (n2 < d.m3) n2 <<= 1;
+  KH_CUDA(c, cudaMalloc(&c->d_bptable, (size_t)n2 * sizeof(BpEntry)));
+  KH_CUDA(c, cudaMalloc(&c->d_aux_tab, 64 * 16 * sizeof(uint32_t)));
+
+  // baby steps: point p = (p+1)*G
+  const uint64_t n_batches = (d.m + KH_GRP - 1) / KH_GRP;
+  const uint64_t T = kh_pick_T(c, n_batches);
+  int rc = kh_ensure_walk_buffers(c, T);
+  if (rc) return rc;
+  WalkSetup ws;
+  memset(&ws, 0, sizeof(ws));
+  u256_set_u64(ws.s, 1);
+  u256_set_u64(ws.k0, 1);
+  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
+  rc = kh_run_setup(c, ws);
+  if (rc) return rc;
+  BsgsTables bt;
+  fill_tables(c, bt);
+  WalkParams wp;
+  wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+  kh_time_begin(c);
+  uint64_t launches = 0;
+  for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
+    wp.batch_base = base;
+    kh_baby_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, bt);
+    launches++;
+  }
+  c->stats.walk_ms += kh_time_end(c);
+  c->stats.walk_launches += launches;
+  c->stats.points += d.m;
+  c->stats.walker_threads = T;
+  KH_CUDA(c, cudaGetLastError());
+
+  // sort + AMP tables
+  kh_time_begin(c);
+  uint64_t other = 0;
+  if (n2 > d.m3) { kh_bp_pad<<<(unsigned)((n2 - d.m3 + 255) / 256), 256, 0, c->stream>>>(c->d_bptable, d.m3, n2); other++; }
+  for (uint64_t kk = 2; kk <= n2; kk <<= 1)
+    for (uint64_t j = kk >> 1; j > 0; j >>= 1) {
+      kh_bitonic_step<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_bptable, n2, j, kk);
+      other++;
+    }
+  kh_amp_kernel<<<1, 64, 0, c->stream>>>(c->d_aux_tab, d.m2, d.m3);
+  other++;
+  c->stats.aux_ms += kh_time_end(c);
+  c->stats.other_launches += other;
+  KH_CUDA(c, cudaGetLastError());
+  c->have_bsgs = true;
+  return KH_OK;
+}
+
+int kh_bsgs_describe(kh_ctx *c, kh_bsgs_desc *out) {
+  if (!c || !out) return KH_EINVAL;
+  if (!c->have_bsgs) return kh_fail(c, KH_ESTATE, "kh_bsgs_build has not run");
+  *out = c->bsgs;
+  return KH_OK;
+}
+
+static int bsgs_region(kh_ctx *c, int tier, int shard, uint8_t **ptr, uint64_t *len) {
+  if (!c->have_bsgs) return kh_fail(c, KH_ESTATE, "kh_bsgs_build has not run");
+  if (tier == 0) { *ptr = reinterpret_cast<uint8_t *>(c->d_bptable); *len = c->bsgs.m3 * sizeof(BpEntry); return KH_OK; }
+  if (tier < 1 || tier > 3 || shard < 0 || shard > 255) return kh_fail(c, KH_EINVAL, "bad tier/shard");
+  *ptr = c->d_tier[tier - 1] + (uint64_t)shard * c->tier_stride[tier - 1];
+  *len = c->bsgs.tier[tier - 1].bytes;
+  return KH_OK;
+}
+
+int kh_bsgs_export(kh_ctx *c, int tier, int shard, void *dst, uint64_t cap) {
+  if (!c || !dst) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  uint8_t *p; uint64_t len;
+  int rc = bsgs_region(c, tier, shard, &p, &len);
+  if (rc) return rc;
+  if (cap < len) return kh_fail(c, KH_EINVAL, "buffer too small (%llu < %llu)", (unsigned long long)cap, (unsigned long long)len);
+  KH_CUDA(c, cudaMemcpyAsync(dst, p, len, cudaMemcpyDeviceToHost, c->stream));
+  KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KH_OK;
+}
+
+int kh_bsgs_import(kh_ctx *c, int tier, int shard, const void *src, uint64_t n) {
+  if (!c || !src) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  uint8_t *p; uint64_t len;
+  int rc = bsgs_region(c, tier, shard, &p, &len);
+  if (rc) return rc;
+  if (n != len) return kh_fail(c, KH_EINVAL, "length mismatch (%llu != %llu)", (unsigned long long)n, (unsigned long long)len);
+  KH_CUDA(c, cudaMemcpyAsync(p, src, len, cudaMemcpyHostToDevice, c->stream));
+  KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KH_OK;
+}
+
+int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_be[32], const uint8_t end_be[32],
+                   uint8_t found_key_be[32], int *found) {
+  if (!c || !pub_xy_be || !start_be || !end_be || !found_key_be || !found) return KH_EINVAL;
+  if (!c->have_bsgs) return kh_fail(c, KH_ESTATE, "kh_bsgs_search before kh_bsgs_build");
+  cudaSetDevice(c->device);
+  *found = 0;
+  const kh_bsgs_desc &d = c->bsgs;
+  u256 start, end;
+  u256_from_be(start, start_be);
+  u256_from_be(end, end_be);
+  // windows: base_w = start + w*2n while base_w < end (keyhunt.cpp:4603-4617)
+  u256 diff;
+  if (kh_sub8(diff.v, end.v, start.v)) return kh_fail(c, KH_EINVAL, "end < start");
+  bool zero = true;
+  for (int i = 0; i < 8; i++) zero &= (diff.v[i] == 0);
+  if (zero) return KH_OK;
+  for (int i = 4; i < 8; i++) if (diff.v[i]) return kh_fail(c, KH_EINVAL, "range wider than 2^128 is not supported");
+  const unsigned __int128 width = ((unsigned __int128)diff.v[3] << 96) | ((unsigned __int128)diff.v[2] << 64) |
+                                  ((unsigned __int128)diff.v[1] << 32) | diff.v[0];
+  const unsigned __int128 step = (unsigned __int128)2 * d.n;
+  const unsigned __int128 windows128 = (width + step - 1) / step;
+  if (windows128 > ((unsigned __int128)1 << 50)) return kh_fail(c, KH_EINVAL, "too many windows");
+  const uint64_t windows = (uint64_t)windows128;
+  const uint64_t cycles = d.aux / 1024 + ((d.aux % 1024) ? 1 : 0);       // keyhunt.cpp:4583
+  // giant steps of consecutive windows are one arithmetic progression; window w covers steps
+  // [w*aux, w*aux + cycles*1024)
+  const uint64_t n_steps = (windows - 1) * d.aux + cycles * 1024;
+  const uint64_t n_batches = (n_steps + KH_GRP - 1) / KH_GRP;
+  const uint64_t T = kh_pick_T(c, n_batches);
+  int rc = kh_ensure_walk_buffers(c, T);
+  if (rc) return rc;
+
+  WalkSetup ws;
+  memset(&ws, 0, sizeof(ws));
+  u256 mm, z;
+  u256_set_u64(mm, d.m);
+  u256_set_u64(z, 0);
+  u256_add_mul64(ws.s, z, mm, 2);                 // step scalar 2m, walked downwards
+  u256_add_mul64(ws.k0, start, mm, 1);            // giant step 0 is Q - (start + m)G
+  ws.neg = 1; ws.T = T; ws.first_batch = 0;
+  for (int i = 0; i < 8; i++) {
+    const uint8_t *px = pub_xy_be + 4 * (7 - i), *py = pub_xy_be + 32 + 4 * (7 - i);
+    ws.q.x.v[i] = ((uint32_t)px[0] << 24) | ((uint32_t)px[1] << 16) | ((uint32_t)px[2] << 8) | px[3];
+    ws.q.y.v[i] = ((uint32_t)py[0] << 24) | ((uint32_t)py[1] << 16) | ((uint32_t)py[2] << 8) | py[3];
+  }
+  ws.q.inf = 0;
+  rc = kh_run_setup(c, ws);
+  if (rc) return rc;
+
+  // candidate queue + result
+  const uint32_t cap = 1u << 16;
+  GiantCand *d_cands = nullptr;
+  uint32_t *d_cnt = nullptr;       // [0] candidate count, [1] found flag
+  u256 *d_key = nullptr;
+  KH_CUDA(c, cudaMalloc(&d_cands, cap * sizeof(GiantCand)));
+  KH_CUDA(c, cudaMalloc(&d_cnt, 4 * sizeof(uint32_t)));
+  KH_CUDA(c, cudaMalloc(&d_key, sizeof(u256)));
+  cudaMemsetAsync(d_cnt, 0, 4 * sizeof(uint32_t), c->stream);
+
+  BsgsTables bt;
+  fill_tables(c, bt);
+  GiantParams gp;
+  gp.tier1 = bt.tier[0]; gp.cands = d_cands; gp.count = d_cnt; gp.cap = cap; gp.pad = 0; gp.n_steps = n_steps;
+  RefineParams rp;
+  rp.bt = bt; rp.aux = c->d_aux_tab; rp.cands = d_cands; rp.n_cands = 0; rp.pad = 0;
+  rp.q = ws.q; rp.start = start; rp.found = d_cnt + 1; rp.found_key = d_key;
+
+  WalkParams wp;
+  wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+
+  int result = KH_OK;
+  uint64_t steps_done = 0;
+  for (uint64_t base = 0; base < n_batches && !*found; base += (uint64_t)wp.steps * T) {
+    wp.batch_base = base;
+    kh_time_begin(c);
+    kh_giant_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, gp);
+    uint32_t h[2] = {0, 0};
+    cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    c->stats.walk_ms += kh_time_end(c);
+    c->stats.walk_launches += 1;
+    const uint64_t covered = std::min<uint64_t>(n_batches - base, (uint64_t)wp.steps * T) * KH_GRP;
+    steps_done += covered;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { result = kh_fail(c, KH_ENODEV, "giant kernel: %s", cudaGetErrorString(e)); break; }
+    if (h[0]) {
+      uint32_t nc = h[0];
+      if (nc > cap) { nc = cap; c->overflowed = true; }
+      c->stats.tier1_positives += h[0];
+      rp.n_cands = nc;
+      kh_time_begin(c);
+      kh_refine_kernel<<<nc, 32, 0, c->stream>>>(rp);
+      cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), c->stream);
+      uint32_t f = 0;
+      cudaMemcpyAsync(&f, d_cnt + 1, sizeof(f), cudaMemcpyDeviceToHost, c->stream);
+      c->stats.aux_ms += kh_time_end(c);
+      c->stats.other_launches += 1;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { result = kh_fail(c, KH_ENODEV, "refine kernel: %s", cudaGetErrorString(e)); break; }
+      if (f) {
+        u256 key;
+        cudaMemcpy(&key, d_key, sizeof(key), cudaMemcpyDeviceToHost);
+        u256_to_be(found_key_be, key);
+        *found = 1;
+      }
+    }
+  }
+  c->stats.points += steps_done;
+  c->stats.walker_threads = T;
+  cudaFree(d_cands); cudaFree(d_cnt); cudaFree(d_key);
+  if (result == KH_OK && c->overflowed) { c->overflowed = false; return kh_fail(c, KH_EOVERFLOW, "tier-1 candidate queue overflowed"); }
+  return result;
+}
+
+}  // extern "C"

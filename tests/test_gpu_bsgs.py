@@ -1,0 +1,74 @@
+"""GPU parity tests for the BSGS path (through the C ABI) against the CPU oracle: byte-identical
+3-tier bloom shards and bP table, identical found keys."""
+import hashlib
+import random
+
+import pytest
+
+from _oracle import N_ORDER, P_FIELD
+
+pytestmark = pytest.mark.gpu
+
+
+def _canon_table(raw):
+    """(6-byte key, index) pairs sorted with ties by index — the reference sort is not stable"""
+    ents = [(raw[i:i + 6], int.from_bytes(raw[i + 8:i + 16], "little")) for i in range(0, len(raw), 16)]
+    return sorted(ents)
+
+
+@pytest.mark.parametrize("n,k", [(1 << 20, 1), (1 << 22, 2), (1 << 24, 4), (1 << 26, 3)])
+def test_bsgs_build_is_byte_identical(kh, oracle, n, k):
+    kh.bsgs_build(n, k)
+    d = kh.bsgs_describe()
+    b = oracle.bsgs_new(n, k)
+    try:
+        p = oracle.bsgs_params(b)
+        assert (d.n, d.m, d.m2, d.m3, d.aux) == (p["n"], p["m"], p["m2"], p["m3"], p["aux"])
+        for tier in (1, 2, 3):
+            assert d.tier[tier - 1].as_dict() == oracle.bloom_desc(oracle.bsgs_bloom(b, tier, 0))
+            for shard in range(256):
+                assert kh.bsgs_export(tier, shard) == oracle.bloom_bytes(oracle.bsgs_bloom(b, tier, shard)), (tier, shard)
+        got = kh.bsgs_export(0)
+        assert _canon_table(got) == _canon_table(oracle.bsgs_table(b))
+        # already canonical on the device: ascending (key, index)
+        assert _canon_table(got) == [(got[i:i + 6], int.from_bytes(got[i + 8:i + 16], "little")) for i in range(0, len(got), 16)]
+    finally:
+        oracle.bsgs_free(b)
+
+
+def test_bsgs_search_finds_planted_keys(kh, oracle):
+    n, k = 1 << 24, 2
+    kh.bsgs_build(n, k)
+    b = oracle.bsgs_new(n, k)
+    try:
+        p = oracle.bsgs_params(b)
+        m, m2, m3 = p["m"], p["m2"], p["m3"]
+        start = 0x8000000000
+        end = start + 40 * 2 * p["n"]
+        rnd = random.Random(3)
+        keys = [start, start + 1, start + m, start + m - 1, start + m + 1, start + 2 * m, end - 1,
+                start + 5 * 2 * m + (2 * 3 + 1) * m2,            # exact tier-2 centre
+                start + 9 * 2 * m + 4 * 2 * m2 + (2 * 7 + 1) * m3,  # exact tier-3 centre (special case keyhunt.cpp:5238)
+                ] + [rnd.randrange(start, end) for _ in range(24)]
+        for key in keys:
+            pub = oracle.pubkey(key)
+            want, _, _ = oracle.bsgs_search(b, pub, start, end)
+            got = kh.bsgs_search(pub, start, end)
+            assert got == want, hex(key)
+            if want is not None:
+                assert want == key
+        # a key outside the range is not found (and the walk ends)
+        pub = oracle.pubkey(end + 10 * p["n"])
+        assert kh.bsgs_search(pub, start, end) == oracle.bsgs_search(b, pub, start, end)[0]
+    finally:
+        oracle.bsgs_free(b)
+
+
+def test_bsgs_reference_fixture_puzzles(kh, oracle):
+    """tests/1to63_65.txt lines 21..32 (puzzle keys) with `-n 0x400000 -k 2 -r 100000:10000000000`; the
+    found keys are the ones the unmodified reference binary printed (tests/golden/README.md)"""
+    kh.bsgs_build(1 << 22, 2)
+    keys = [0x1ba534, 0x2de40f, 0x556e52, 0xdc2a04, 0x1fa5ee5, 0x340326e, 0x6ac3875, 0xd916ce8, 0x17e2551e, 0x3d94cd64,
+            0x7d4fe747, 0xb862a62e]
+    for key in keys:
+        assert kh.bsgs_search(oracle.pubkey(key), 0x100000, 0x10000000000) == key
