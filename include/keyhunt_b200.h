@@ -122,6 +122,10 @@ typedef struct {
 } kh_stats;
 int kh_get_stats(kh_ctx *ctx, kh_stats *out, int reset);
 int kh_device_info(kh_ctx *ctx, char *name, int name_cap, int *sm_count, uint64_t *hbm_bytes);
+/* integer-pipe micro-benchmarks (thread-level ops/s over the whole chip), the measured denominators of
+ * the integer roofline: [0] IADD3, [1] LOP3, [2] SHF, [3] IMAD, [4] IMAD.WIDE.U32.X (fe_mul row),
+ * [5] LOP3+IMAD issued together (both integer pipes) */
+int kh_int_peak(kh_ctx *ctx, double out_ops_per_s[6]);
 
 #ifdef __cplusplus
 }

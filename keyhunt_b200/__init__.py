@@ -30,7 +30,7 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 EXPORTS = ["kh_create", "kh_destroy", "kh_last_error", "kh_set_option", "kh_bloom_params", "kh_set_targets",
            "kh_get_bloom", "kh_get_table", "kh_scan", "kh_poll_hits", "kh_derive", "kh_bsgs_build",
            "kh_bsgs_describe", "kh_bsgs_export", "kh_bsgs_import", "kh_bsgs_search", "kh_get_stats",
-           "kh_device_info"]
+           "kh_device_info", "kh_int_peak"]
 
 
 class KhError(RuntimeError):
@@ -130,6 +130,7 @@ def load_library(path=None):
     L.kh_bsgs_search.argtypes = [vp, u8p, u8p, u8p, u8p, C.POINTER(C.c_int)]
     L.kh_get_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
     L.kh_device_info.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(u64)]
+    L.kh_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name not in ("kh_destroy", "kh_last_error"):
             getattr(L, name).restype = C.c_int
@@ -260,6 +261,12 @@ class KeyHunt:
         self._ck(self._lib.kh_bsgs_search(self._h, _be32(pub[0]) + _be32(pub[1]), _be32(start), _be32(end), out,
                                           C.byref(found)))
         return int.from_bytes(out.raw, "big") if found.value else None
+
+    def int_peak(self):
+        """measured integer-pipe peaks, thread-ops/s over the whole chip"""
+        arr = (C.c_double * 6)()
+        self._ck(self._lib.kh_int_peak(self._h, arr))
+        return dict(zip(["iadd3", "lop3", "shf", "imad", "imad_wide", "lop3_imad_mix"], [float(x) for x in arr]))
 
     def stats(self, reset=False):
         s = Stats()

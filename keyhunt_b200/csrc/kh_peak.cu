@@ -1,0 +1,80 @@
+// kh_peak.cu — integer-pipe micro-benchmarks: the measured denominators of the integer roofline
+// (SURVEY §8d asks for an IMAD/IADD3/LOP3 micro-benchmark on the box next to MEASURED_PEAKS.json).
+// Each kernel runs 16 independent dependency chains per thread so that the pipes, not latency, bound it.
+#include "kh_ctx.cuh"
+
+#define PEAK_ITERS 4096
+#define PEAK_CHAINS 16
+
+template <int KIND>
+__global__ void __launch_bounds__(256) kh_peak_kernel(uint32_t *out, uint32_t seed) {
+  uint32_t a[PEAK_CHAINS], b[PEAK_CHAINS];
+#pragma unroll
+  for (int i = 0; i < PEAK_CHAINS; i++) { a[i] = seed + threadIdx.x * 977u + i; b[i] = seed * 31u + blockIdx.x + i * 7u; }
+  const uint32_t x = seed ^ (threadIdx.x * 2654435761u);
+  uint32_t row[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) row[i][k] = x + 9 * i + k;
+#pragma unroll 1
+  for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; i++) {
+      if (KIND == 0) {          // IADD3 : a = a + b + it
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(a[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 1) {   // LOP3  : a = (a & b) ^ it
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(a[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 2) {   // SHF   : a = rotl(a, 7) (funnel shift with itself)
+        asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i]));
+      } else if (KIND == 3) {   // IMAD  : a = a * b + it
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 4) {   // IMAD.WIDE.U32.X : one row of fe_mul_wide (4 wide multiply-adds with carry) per step
+        if (i < 4) kh::kh_mad_row(row[i], a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], row[i][0] | 1u);
+      } else {                  // MIX   : one ALU-pipe op (LOP3) + one FMA-pipe op (IMAD) per chain step
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(a[i]) : "r"(b[i]), "r"(it));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(a[i]), "r"(it));
+      }
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < PEAK_CHAINS; i++) r ^= a[i] ^ b[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) r ^= row[i][k];
+  if (r == 0x12345678u) out[0] = r;   // keeps the chains alive
+}
+
+template <int KIND>
+static double run_peak(kh_ctx *c, uint32_t *d_out, int ops_per_step) {
+  const int blocks = c->sm_count * 8;
+  kh_peak_kernel<KIND><<<blocks, 256, 0, c->stream>>>(d_out, 12345u);   // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    kh_time_begin(c);
+    kh_peak_kernel<KIND><<<blocks, 256, 0, c->stream>>>(d_out, 12345u + rep);
+    const double ms = kh_time_end(c);
+    const double ops = (double)blocks * 256.0 * PEAK_ITERS * PEAK_CHAINS * ops_per_step;
+    best = std::max(best, ops / (ms * 1e-3));
+  }
+  return best;
+}
+
+extern "C" int kh_int_peak(kh_ctx *c, double out_ops_per_s[6]) {
+  if (!c || !out_ops_per_s) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  uint32_t *d_out = nullptr;
+  KH_CUDA(c, cudaMalloc(&d_out, 64));
+  out_ops_per_s[0] = run_peak<0>(c, d_out, 1);
+  out_ops_per_s[1] = run_peak<1>(c, d_out, 1);
+  out_ops_per_s[2] = run_peak<2>(c, d_out, 1);
+  out_ops_per_s[3] = run_peak<3>(c, d_out, 1);
+  out_ops_per_s[4] = run_peak<4>(c, d_out, 1);   // 16 IMAD.WIDE per loop trip = 16 "chain steps"
+  out_ops_per_s[5] = run_peak<5>(c, d_out, 2);
+  cudaFree(d_out);
+  c->stats.other_launches += 24;
+  KH_CUDA(c, cudaGetLastError());
+  return KH_OK;
+}
