@@ -1,0 +1,129 @@
+"""CPU: the product's device headers (keyhunt_b200/csrc/*.cuh) compiled for the host (tests/devsim) agree
+with the oracle: limb arithmetic, message packers, hashes, bloom index arithmetic, batch geometry with
+interleaved walker threads and multi-launch continuation, and the fused scan/emit logic."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+from _oracle import (CRYPTO_BTC, CRYPTO_ETH, MODE_ADDRESS, MODE_RMD160, MODE_XPOINT, N_ORDER, P_FIELD, SEARCH_BOTH,
+                     SEARCH_COMPRESS, SEARCH_UNCOMPRESS, be32)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class DsHit(C.Structure):
+    _fields_ = [("index", C.c_uint64), ("kind", C.c_uint32), ("matched", C.c_uint8 * 20), ("pad", C.c_uint32)]
+
+
+@pytest.fixture(scope="module")
+def ds():
+    d = os.path.join(HERE, "devsim")
+    subprocess.check_call(["make", "-C", d], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(d, "libkh_devsim.so"))
+    lib.ds_xxh64_20.restype = C.c_uint64; lib.ds_xxh64_20.argtypes = [C.c_char_p, C.c_uint64]
+    lib.ds_xxh64_32.restype = C.c_uint64; lib.ds_xxh64_32.argtypes = [C.c_char_p, C.c_uint64]
+    lib.ds_bloom_mod.restype = C.c_uint64; lib.ds_bloom_mod.argtypes = [C.c_uint64, C.c_uint64]
+    lib.ds_scan.restype = C.c_int64
+    lib.ds_scan.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint32, C.c_char_p, C.c_char_p,
+                            C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(DsHit), C.c_uint32]
+    lib.ds_walk_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_char_p]
+    return lib
+
+
+def _f2(fn, a, b):
+    o = C.create_string_buffer(32); fn(be32(a), be32(b), o); return int.from_bytes(o.raw, "big")
+
+
+def _f1(fn, a):
+    o = C.create_string_buffer(32); fn(be32(a), o); return int.from_bytes(o.raw, "big")
+
+
+def test_field_limb_algorithms(ds):
+    rnd = random.Random(7)
+    P = P_FIELD
+    edge = [0, 1, 2, P - 1, P - 2, 2**255, (1 << 224) - 1, 2**32, 2**32 + 977, P - 977, 0xFFFFFFFF, P - 2**32, 2**256 - 2**33]
+    vals = [e % P for e in edge] + [rnd.randrange(P) for _ in range(400)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        assert _f2(ds.ds_fe_mul, a, b) == a * b % P
+        assert _f2(ds.ds_fe_add, a, b) == (a + b) % P
+        assert _f2(ds.ds_fe_sub, a, b) == (a - b) % P
+        assert _f1(ds.ds_fe_sqr, a) == a * a % P
+    for a in vals[:24]:
+        assert _f1(ds.ds_fe_inv, a) == pow(a, P - 2, P)
+
+
+def test_scalar_mult_and_hashes(ds, oracle):
+    rnd = random.Random(8)
+    for k in [1, 2, 3, 0xDEADBEEF, N_ORDER - 1] + [rnd.randrange(1, N_ORDER) for _ in range(6)]:
+        o = C.create_string_buffer(64); ds.ds_pubkey(be32(k), o)
+        assert (int.from_bytes(o.raw[:32], "big"), int.from_bytes(o.raw[32:], "big")) == oracle.pubkey(k)
+    out = C.create_string_buffer(20)
+    for _ in range(200):
+        x, y = rnd.randrange(P_FIELD), rnd.randrange(P_FIELD)
+        for pre in (2, 3):
+            ds.ds_hash160_comp(pre, be32(x), out); assert out.raw == oracle.hash160_comp(pre, x)
+        ds.ds_hash160_uncomp(be32(x) + be32(y), out); assert out.raw == oracle.hash160_uncomp(x, y)
+        ds.ds_eth_addr(be32(x) + be32(y), out); assert out.raw == oracle.eth_addr(x, y)
+        d, s = rnd.randbytes(32), rnd.randrange(2**64)
+        assert ds.ds_xxh64_20(d[:20], s) == oracle.xxh64(d[:20], s)
+        assert ds.ds_xxh64_32(d, s) == oracle.xxh64(d, s)
+
+
+def test_bloom_exact_modulo(ds):
+    rnd = random.Random(9)
+    for _ in range(20000):
+        bits = rnd.choice([287551, 28755175, 241215892, 7537996, 2**20, 2**33 + 5, rnd.randrange(2, 2**40), 3, 2**63 + 11, 2**64 - 1])
+        x = rnd.choice([rnd.randrange(2**64), 2**64 - 1, (bits * 5) % 2**64, (bits * 5 - 1) % 2**64, 0, bits - 1, bits])
+        assert ds.ds_bloom_mod(x, bits) == x % bits
+
+
+@pytest.mark.parametrize("start,stride,nb,T,spl", [(1, 1, 5, 3, 2), (0x8000000000, 1, 4, 4, 1), (0xABCDEF0123456789ABCDEF, 0x1F3, 3, 2, 5),
+                                                     (12345, 7, 7, 3, 1)])
+def test_walk_geometry(ds, oracle, start, stride, nb, T, spl):
+    """interleaved walker threads (batch t, t+T, ...), several launches, ragged tail == the reference's batches"""
+    out = C.create_string_buffer(nb * 1024 * 64)
+    ds.ds_walk_dump(be32(start), be32(stride), nb, T, spl, out)
+    for b in range(nb):
+        assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(start + b * 1024 * stride, stride, True)
+
+
+KINDS = {"xpoint": (0, MODE_XPOINT, CRYPTO_BTC, SEARCH_COMPRESS), "comp": (1, MODE_RMD160, CRYPTO_BTC, SEARCH_COMPRESS),
+         "uncomp": (2, MODE_RMD160, CRYPTO_BTC, SEARCH_UNCOMPRESS), "both": (3, MODE_ADDRESS, CRYPTO_BTC, SEARCH_BOTH),
+         "eth": (4, MODE_ADDRESS, CRYPTO_ETH, SEARCH_COMPRESS)}
+
+
+@pytest.mark.parametrize("name", sorted(KINDS))
+def test_scan_emit_logic(ds, oracle, name):
+    kind, mode, crypto, search = KINDS[name]
+    rnd = random.Random(hash(name) & 0xFFFF)
+    start, stride, nb, T = 0x2000000000000777, 3, 6, 4
+    n = nb * 1024
+    recs = []
+    for j, i in enumerate(sorted({0, 511, 512, 513, 1023, 1024, n - 1} | {rnd.randrange(n) for _ in range(10)})):
+        x, y = oracle.pubkey(start + i * stride)
+        if name == "xpoint":
+            recs.append(be32(x)[:20])
+        elif name == "eth":
+            recs.append(oracle.eth_addr(x, y))
+        elif name == "comp":
+            recs.append(oracle.hash160_comp((2 + (y & 1)) if j % 3 else (3 - (y & 1)), x))
+        elif name == "uncomp":
+            recs.append(oracle.hash160_uncomp(x, y))
+        else:
+            recs.append(oracle.hash160_uncomp(x, y) if j % 2 else oracle.hash160_comp(2 + (y & 1), x))
+    recs += [rnd.randbytes(20) for _ in range(100)]
+    t = oracle.targets_new(b"".join(recs))
+    want = oracle.scan(t, mode, crypto, search, start, stride, n, nthreads=2)
+    bl = oracle.targets_bloom(t)
+    d = oracle.bloom_desc(bl)
+    hits = (DsHit * 256)()
+    cnt = ds.ds_scan(kind, oracle.targets_table(t), len(recs), oracle.bloom_bytes(bl), d["bits"], d["hashes"], be32(start),
+                     be32(stride), nb, T, 2, hits, 256)
+    oracle.targets_free(t)
+    got = sorted((hits[i].index, hits[i].kind, bytes(hits[i].matched)) for i in range(cnt))
+    assert got == sorted((h["index"], h["kind"], h["matched"]) for h in want)
+    assert cnt >= 10
