@@ -272,6 +272,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-per-launch", type=int, default=0, help="library option (profiling runs use 1 for short kernels)")
+    ap.add_argument("--step-points-log2", type=int, default=32, help="keys per step = 2^this (profiling runs use less)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -299,6 +301,10 @@ def main():
     w = WORKLOADS[wl]
     Ksteps, W = args.steps, args.warmup
     kh = K.KeyHunt(local)
+    if args.steps_per_launch:
+        kh.set_option("steps_per_launch", args.steps_per_launch)
+    global STEP_POINTS
+    STEP_POINTS = 1 << args.step_points_log2
     info = kh.device_info()
     mode, crypto, search = kh_modes(K, wl)
 
