@@ -18,7 +18,7 @@ __all__ = ["KeyHunt", "KhError", "Hit", "KeyInfo", "BloomDesc", "BsgsDesc", "Sta
            "HIT_COMP02", "HIT_COMP03", "HIT_UNCOMP", "HIT_ETH", "HIT_XPOINT", "N_ORDER", "parse_targets"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkh_b200.so")
+LIB_PATH = os.environ.get("KH_B200_LIB") or os.path.join(_HERE, "libkh_b200.so")   # env override: A/B builds when tuning
 
 # keyhunt.cpp:76-90
 MODE_XPOINT, MODE_ADDRESS, MODE_BSGS, MODE_RMD160 = 0, 1, 2, 3

@@ -75,16 +75,15 @@ struct ScanEmit {
       for (int i = 0; i < 5; i++) h[i] = bswap32(x.v[7 - i]);
       probe(h, KH_KIND_XPOINT, batch, idx);
     }
-    if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_BOTH) {  // both prefixes for every X, keyhunt.cpp:3493-3494
+    if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {
+      // jobs 0,1 = prefixes 02,03 (hashed for EVERY X, keyhunt.cpp:3493-3494), job 2 = uncompressed (:3519);
+      // one static copy of the hash + probe code, looped
+      const int j0 = (KIND == KH_SCAN_UNCOMP) ? 2 : 0, j1 = (KIND == KH_SCAN_COMP) ? 2 : 3;
 #pragma unroll 1
-      for (uint32_t pre = 2; pre <= 3; pre++) {
-        hash160_compressed(h, pre, x);
-        probe(h, pre == 2 ? KH_KIND_COMP02 : KH_KIND_COMP03, batch, idx);
+      for (int job = j0; job < j1; job++) {
+        hash160_job<NEED_Y>(h, job, x, y);
+        probe(h, (uint32_t)job, batch, idx);   // KH_KIND_COMP02 = 0, COMP03 = 1, UNCOMP = 2
       }
-    }
-    if (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {  // keyhunt.cpp:3519
-      hash160_uncompressed(h, x, y);
-      probe(h, KH_KIND_UNCOMP, batch, idx);
     }
     if (KIND == KH_SCAN_ETH) {                           // keyhunt.cpp:3540
       eth_address(h, x, y);

@@ -49,18 +49,42 @@ KH_HD uint32_t bswap32(uint32_t x) {
 }
 KH_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
+
+// ---- pipe balancing ---------------------------------------------------------------------------------
+// SHA-256 / RIPEMD-160 are pure ALU-pipe code (SHF, LOP3, IADD3).  kh_addf(a, b) computes a + b as IMAD
+// a*1+b with the 1 taken from constant memory (so ptxas cannot fold it back into an IADD), which moves the
+// addition onto the FMA-heavy pipe.  Measured on B200 (kh_hash_peak, tools_hashpeak.py): SHA-256 alone gains
+// 15 % (13.9 -> 16.0 G compressions/s) but RIPEMD-160 loses 37 % (28.3 -> 17.7 G/s, it has more adds than
+// logic ops, so the IMADs become the bottleneck) and the fused scan kernels lose 2-4 % (they already keep the
+// FMA-heavy pipe 50-70 % busy with IMAD.WIDE field multiplications).  Hence OFF by default; kept for A/B.
+#ifndef KH_FMA_ADDS
+#define KH_FMA_ADDS 0
+#endif
+#if defined(__CUDACC__)
+static __constant__ uint32_t kh_c_one = 1u;
+#endif
+KH_HD uint32_t kh_addf(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && KH_FMA_ADDS
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(kh_c_one), "r"(b));
+  return r;
+#else
+  return a + b;
+#endif
+}
+
 #define KH_SHA_S0(x) (rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22))
 #define KH_SHA_S1(x) (rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25))
 #define KH_SHA_s0(x) (rotr32(x, 7) ^ rotr32(x, 18) ^ ((x) >> 3))
 #define KH_SHA_s1(x) (rotr32(x, 17) ^ rotr32(x, 19) ^ ((x) >> 10))
 #define KH_SHA_CH(x, y, z) (((x) & (y)) ^ (~(x) & (z)))
 #define KH_SHA_MAJ(x, y, z) (((x) & (y)) ^ ((x) & (z)) ^ ((y) & (z)))
-#define KH_SHA_RND(a, b, c, d, e, f, g, h, k, wv)                      \
-  {                                                                    \
-    uint32_t t1 = h + KH_SHA_S1(e) + KH_SHA_CH(e, f, g) + (k) + (wv);  \
-    uint32_t t2 = KH_SHA_S0(a) + KH_SHA_MAJ(a, b, c);                  \
-    d += t1;                                                           \
-    h = t1 + t2;                                                       \
+#define KH_SHA_RND(a, b, c, d, e, f, g, h, k, wv)                                   \
+  {                                                                                 \
+    uint32_t t1 = kh_addf(kh_addf(h + (k) + (wv), KH_SHA_S1(e)), KH_SHA_CH(e, f, g)); \
+    uint32_t t2 = kh_addf(KH_SHA_S0(a), KH_SHA_MAJ(a, b, c));                       \
+    d = kh_addf(d, t1);                                                             \
+    h = kh_addf(t1, t2);                                                            \
   }
 
 #define KH_RMD_F0(x, y, z) ((x) ^ (y) ^ (z))
@@ -68,18 +92,53 @@ KH_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 #define KH_RMD_F2(x, y, z) (((x) | ~(y)) ^ (z))
 #define KH_RMD_F3(x, y, z) (((x) & (z)) | ((y) & ~(z)))
 #define KH_RMD_F4(x, y, z) ((x) ^ ((y) | ~(z)))
-#define KH_RMD_STEP(F, a, b, c, d, e, xv, k, s)      \
-  {                                                  \
-    a = rotl32(a + F(b, c, d) + (xv) + (k), s) + e;  \
-    c = rotl32(c, 10);                               \
+#define KH_RMD_STEP(F, a, b, c, d, e, xv, k, s)                         \
+  {                                                                     \
+    a = kh_addf(rotl32(kh_addf(kh_addf(a, F(b, c, d)), (xv) + (k)), s), e); \
+    c = rotl32(c, 10);                                                  \
   }
+
+#define KH_SHA_K_LIST                                                                               \
+  0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, \
+  0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, \
+  0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, \
+  0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, \
+  0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, \
+  0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, \
+  0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, \
+  0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u
+#if defined(__CUDACC__)
+static __constant__ uint32_t kh_sha_k_dev[64] = {KH_SHA_K_LIST};
+#endif
+static const uint32_t kh_sha_k_host[64] = {KH_SHA_K_LIST};
+KH_HD uint32_t sha_k(int i) {
+#ifdef __CUDA_ARCH__
+  return kh_sha_k_dev[i];
+#else
+  return kh_sha_k_host[i];
+#endif
+}
 
 #include "hash_rounds.inc"
 
 // one SHA-256 compression; w[] is consumed (used as the circular schedule)
+// KH_SHA_ROLLED: 4 trips of 16 rounds (round constants from constant memory) instead of 64 unrolled
+// rounds: 3.5x less code.  The scan kernels are instruction-fetch sensitive (ncu: stall no_instruction),
+// so the hot loop must stay inside the SM instruction cache.
+#ifndef KH_SHA_ROLLED
+#define KH_SHA_ROLLED 1
+#endif
 KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16]) {
   uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#if KH_SHA_ROLLED
+#pragma unroll 1
+  for (int kb = 0; kb < 64; kb += 16) {
+    if (kb) { KH_SHA256_EXPAND16(w); }
+    KH_SHA256_ROUNDS16(a, b, c, d, e, f, g, h, w, kb);
+  }
+#else
   KH_SHA256_ROUNDS(a, b, c, d, e, f, g, h, w);
+#endif
   st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 KH_HD void sha256_init(uint32_t st[8]) {
@@ -137,6 +196,43 @@ KH_HD void hash160_uncompressed(uint32_t out[5], const fe &x, const fe &y) {
   for (int i = 1; i < 15; i++) w[i] = 0;
   w[15] = 0x208u;
   sha256_compress(st, w);
+  ripemd160_of_sha(out, st);
+}
+
+// One hash160 "job" with a single static copy of the SHA-256 and RIPEMD-160 bodies, whatever the job:
+// job 0 / 1 = compressed key with prefix 02 / 03 (one block), job 2 = uncompressed key 04||X||Y (two
+// blocks; only when WITH_UNCOMP).  The scan kernel loops over jobs with `#pragma unroll 1`, so its hot
+// loop holds each hash body once (instruction-cache footprint, see sha256_compress).
+template <bool WITH_UNCOMP>
+KH_HD void hash160_job(uint32_t out[5], int job, const fe &x, const fe &y) {
+  uint32_t w[16], st[8];
+  sha256_init(st);
+  const bool unc = WITH_UNCOMP && (job == 2);
+  const int nblk = unc ? 2 : 1;
+#pragma unroll 1
+  for (int blk = 0; blk < nblk; blk++) {
+    if (blk == 0) {
+      const uint32_t pre = unc ? 4u : (2u + (uint32_t)job);
+      w[0] = (pre << 24) | (x.v[7] >> 8);
+#pragma unroll
+      for (int i = 1; i < 8; i++) w[i] = shr8_pair(x.v[8 - i], x.v[7 - i]);
+      if (unc) {
+        w[8] = shr8_pair(x.v[0], y.v[7]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) w[8 + i] = shr8_pair(y.v[8 - i], y.v[7 - i]);
+      } else {
+        w[8] = (x.v[0] << 24) | 0x00800000u;
+        w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0; w[14] = 0;
+        w[15] = 0x108u;
+      }
+    } else {
+      w[0] = (y.v[0] << 24) | 0x00800000u;
+#pragma unroll
+      for (int i = 1; i < 15; i++) w[i] = 0;
+      w[15] = 0x208u;
+    }
+    sha256_compress(st, w);
+  }
   ripemd160_of_sha(out, st);
 }
 

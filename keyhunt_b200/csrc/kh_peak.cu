@@ -2,6 +2,7 @@
 // (SURVEY §8d asks for an IMAD/IADD3/LOP3 micro-benchmark on the box next to MEASURED_PEAKS.json).
 // Each kernel runs 16 independent dependency chains per thread so that the pipes, not latency, bound it.
 #include "kh_ctx.cuh"
+#include "hash.cuh"
 
 #define PEAK_ITERS 4096
 #define PEAK_CHAINS 16
@@ -75,6 +76,54 @@ extern "C" int kh_int_peak(kh_ctx *c, double out_ops_per_s[6]) {
   out_ops_per_s[5] = run_peak<5>(c, d_out, 2);
   cudaFree(d_out);
   c->stats.other_launches += 24;
+  KH_CUDA(c, cudaGetLastError());
+  return KH_OK;
+}
+
+// ---- hash micro-benchmarks: SHA-256 compressions / RIPEMD-160 blocks per second in isolation -----------
+template <int WHICH>
+__global__ void __launch_bounds__(256) kh_hash_bench(uint32_t *out, uint32_t seed, int iters) {
+  uint32_t st[8], w[16], h[5];
+#pragma unroll
+  for (int i = 0; i < 8; i++) st[i] = seed + threadIdx.x * 31u + i;
+#pragma unroll
+  for (int i = 0; i < 5; i++) h[i] = 0;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    if (WHICH == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) w[i] = st[i & 7] ^ (uint32_t)(it + i);
+      kh::sha256_compress(st, w);
+    } else {
+      kh::ripemd160_of_sha(h, st);
+#pragma unroll
+      for (int i = 0; i < 5; i++) st[i] ^= h[i];
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r ^= st[i];
+  if (r == 0x12345678u) out[0] = r;
+}
+
+extern "C" int kh_hash_peak(kh_ctx *c, int blocks_per_sm, double out_blocks_per_s[2]) {
+  if (!c || !out_blocks_per_s || blocks_per_sm < 1) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  uint32_t *d_out = nullptr;
+  KH_CUDA(c, cudaMalloc(&d_out, 64));
+  const int blocks = c->sm_count * blocks_per_sm, iters = 2000;
+  for (int which = 0; which < 2; which++) {
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+      kh_time_begin(c);
+      if (which == 0) kh_hash_bench<0><<<blocks, 256, 0, c->stream>>>(d_out, 7u + rep, iters);
+      else kh_hash_bench<1><<<blocks, 256, 0, c->stream>>>(d_out, 7u + rep, iters);
+      const double ms = kh_time_end(c);
+      if (rep) best = std::max(best, (double)blocks * 256.0 * iters / (ms * 1e-3));
+    }
+    out_blocks_per_s[which] = best;
+  }
+  cudaFree(d_out);
   KH_CUDA(c, cudaGetLastError());
   return KH_OK;
 }
