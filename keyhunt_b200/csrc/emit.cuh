@@ -59,6 +59,10 @@ struct ScanTargets {
 template <int KIND>
 struct ScanEmit {
   static constexpr bool NEED_Y = (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH || KIND == KH_SCAN_ETH);  // keyhunt.cpp:3294
+#ifndef KH_OUTLINE_MUL
+#define KH_OUTLINE_MUL 1
+#endif
+  static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT);
   const ScanTargets &tg;
   KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
 
@@ -108,6 +112,7 @@ struct BsgsTables {
 // baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
 struct BabyEmit {
   static constexpr bool NEED_Y = false;
+  static constexpr bool OUTLINE_MUL = false;
   const BsgsTables &bt;
   KH_HDM explicit BabyEmit(const BsgsTables &b) : bt(b) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
@@ -150,6 +155,7 @@ struct GiantParams {
 };
 struct GiantEmit {
   static constexpr bool NEED_Y = false;
+  static constexpr bool OUTLINE_MUL = false;
   const GiantParams &gp;
   KH_HDM explicit GiantEmit(const GiantParams &g) : gp(g) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {

@@ -250,6 +250,24 @@ KH_HD void fe_mul(fe &r, const fe &a, const fe &b) {
 }
 KH_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
 
+// Out-of-line multiply: the hash-heavy scan kernels are instruction-fetch bound (ncu: stall no_instruction,
+// GPC instruction-cache requests at >90 % of peak), so their EC loop calls ONE shared copy of the multiplier
+// instead of inlining ~2.4 KB of code at each of its eight call sites.  Operands travel by value (registers).
+#if defined(__CUDACC__)
+static __device__ __noinline__ fe fe_mul_ol(fe a, fe b) {
+  fe r;
+  fe_mul(r, a, b);
+  return r;
+}
+#endif
+template <bool OUTLINE>
+KH_HD void fe_mul_sel(fe &r, const fe &a, const fe &b) {
+#if defined(__CUDA_ARCH__)
+  if (OUTLINE) { r = fe_mul_ol(a, b); return; }
+#endif
+  fe_mul(r, a, b);
+}
+
 // r = a^(2^n)
 KH_HD void fe_sqr_n(fe &r, const fe &a, int n) {
   r = a;
@@ -259,6 +277,20 @@ KH_HD void fe_sqr_n(fe &r, const fe &a, int n) {
 
 // a^(P-2): 255 squarings + 15 multiplications (addition chain over the run-lengths of P-2:
 // 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1).  inv(0) = 0, like Int::ModInv's "no inverse" result.
+// Cold code (once per 1024 points): on the device every multiply goes through the shared out-of-line copy
+// so that the inversion does not flush the hot loop out of the instruction cache.
+KH_HD void fe_mul_cold(fe &r, const fe &a, const fe &b) {
+#if defined(__CUDA_ARCH__)
+  r = fe_mul_ol(a, b);
+#else
+  fe_mul(r, a, b);
+#endif
+}
+KH_HD void fe_sqr_n_cold(fe &r, const fe &a, int n) {
+  r = a;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) fe_mul_cold(r, r, r);
+}
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
@@ -266,21 +298,21 @@ static
 #endif
 void fe_inv(fe &r, const fe &a) {
   fe x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223, t;
-  fe_sqr(x2, a); fe_mul(x2, x2, a);
-  fe_sqr(x3, x2); fe_mul(x3, x3, a);
-  fe_sqr_n(x6, x3, 3); fe_mul(x6, x6, x3);
-  fe_sqr_n(x9, x6, 3); fe_mul(x9, x9, x3);
-  fe_sqr_n(x11, x9, 2); fe_mul(x11, x11, x2);
-  fe_sqr_n(x22, x11, 11); fe_mul(x22, x22, x11);
-  fe_sqr_n(x44, x22, 22); fe_mul(x44, x44, x22);
-  fe_sqr_n(x88, x44, 44); fe_mul(x88, x88, x44);
-  fe_sqr_n(x176, x88, 88); fe_mul(x176, x176, x88);
-  fe_sqr_n(x220, x176, 44); fe_mul(x220, x220, x44);
-  fe_sqr_n(x223, x220, 3); fe_mul(x223, x223, x3);
-  fe_sqr_n(t, x223, 23); fe_mul(t, t, x22);
-  fe_sqr_n(t, t, 5); fe_mul(t, t, a);
-  fe_sqr_n(t, t, 3); fe_mul(t, t, x2);
-  fe_sqr_n(t, t, 2); fe_mul(r, t, a);
+  fe_mul_cold(x2, a, a); fe_mul_cold(x2, x2, a);
+  fe_mul_cold(x3, x2, x2); fe_mul_cold(x3, x3, a);
+  fe_sqr_n_cold(x6, x3, 3); fe_mul_cold(x6, x6, x3);
+  fe_sqr_n_cold(x9, x6, 3); fe_mul_cold(x9, x9, x3);
+  fe_sqr_n_cold(x11, x9, 2); fe_mul_cold(x11, x11, x2);
+  fe_sqr_n_cold(x22, x11, 11); fe_mul_cold(x22, x22, x11);
+  fe_sqr_n_cold(x44, x22, 22); fe_mul_cold(x44, x44, x22);
+  fe_sqr_n_cold(x88, x44, 44); fe_mul_cold(x88, x88, x44);
+  fe_sqr_n_cold(x176, x88, 88); fe_mul_cold(x176, x176, x88);
+  fe_sqr_n_cold(x220, x176, 44); fe_mul_cold(x220, x220, x44);
+  fe_sqr_n_cold(x223, x220, 3); fe_mul_cold(x223, x223, x3);
+  fe_sqr_n_cold(t, x223, 23); fe_mul_cold(t, t, x22);
+  fe_sqr_n_cold(t, t, 5); fe_mul_cold(t, t, a);
+  fe_sqr_n_cold(t, t, 3); fe_mul_cold(t, t, x2);
+  fe_sqr_n_cold(t, t, 2); fe_mul_cold(r, t, a);
 }
 
 // ---- (de)serialisation -------------------------------------------------------------------------------

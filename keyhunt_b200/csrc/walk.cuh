@@ -90,6 +90,7 @@ KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
 // range is batch*1024 + idx; y is valid only if Emit::NEED_Y.
 template <class Emit>
 KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
+  constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
@@ -106,7 +107,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       fe gx, dx;
       tab_load_x(gx, tab, e);
       fe_sub(dx, gx, px);
-      if (e == 0) acc = dx; else fe_mul(acc, acc, dx);
+      if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
     fe inv;
@@ -120,9 +121,9 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e > 0) {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
-        fe_mul(dinv, pre, inv);       // 1/dx_e
+        fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
-        fe_mul(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
+        fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
       } else {
         dinv = inv;
       }
@@ -138,19 +139,19 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
           fe s, dy, s2;
           if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
-          fe_mul(s, dy, dinv);
-          fe_sqr(s2, s);
+          fe_mul_sel<OL>(s, dy, dinv);
+          fe_mul_sel<OL>(s2, s, s);
           fe_sub(x3, s2, px);
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
-            fe_sub(y3, gx, x3); fe_mul(y3, y3, s); fe_sub(y3, y3, gy);
+            fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
             px = x3; py = y3;
             do_emit = false;
             idx = 0;
           } else {
             if (Emit::NEED_Y) {
-              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
-              else          { fe_sub(y3, x3, gx); fe_mul(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
+              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
+              else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
             } else {
               y3 = py;
             }

@@ -111,6 +111,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
 // all X (and Y) of the first n_batches batches, in range order: out[(b*1024+i)*64]
 struct DumpEmit {
   static constexpr bool NEED_Y = true;
+  static constexpr bool OUTLINE_MUL = false;
   uint8_t *out;
   void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
     uint8_t *p = out + (batch * KH_GRP + idx) * 64;
