@@ -111,6 +111,75 @@ KH_HD void kh_mad_row(uint32_t *acc, uint32_t a0, uint32_t a2, uint32_t a4, uint
   acc[8] += (uint32_t)c;
 #endif
 }
+// acc[0..2N-1] += x[k]*y[k] as N adjacent 64-bit lanes (k < N <= 4); the carry-out is added into acc[2N]
+template <int N>
+KH_HD void kh_mad_chain(uint32_t *acc, const uint32_t *x, const uint32_t *y) {
+#ifdef __CUDA_ARCH__
+  if (N == 1) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(x[0]), "r"(y[0]));
+  } else if (N == 2) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\tmadc.hi.cc.u32 %3, %6, %8, %3;\n\taddc.u32 %4, %4, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+        : "r"(x[0]), "r"(x[1]), "r"(y[0]), "r"(y[1]));
+  } else if (N == 3) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %11, %2;\n\tmadc.hi.cc.u32 %3, %8, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\taddc.u32 %6, %6, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(y[0]), "r"(y[1]), "r"(y[2]));
+  } else {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %14, %2;\n\tmadc.hi.cc.u32 %3, %10, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %15, %4;\n\tmadc.hi.cc.u32 %5, %11, %15, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %16, %6;\n\tmadc.hi.cc.u32 %7, %12, %16, %7;\n\taddc.u32 %8, %8, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+  }
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < N; k++) {
+    uint64_t p = (uint64_t)x[k] * y[k];
+    uint64_t t = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+    acc[2 * k] = (uint32_t)t; c = t >> 32;
+    t = (uint64_t)acc[2 * k + 1] + (p >> 32) + c;
+    acc[2 * k + 1] = (uint32_t)t; c = t >> 32;
+  }
+  acc[2 * N] += (uint32_t)c;
+#endif
+}
+// r[0..15] = 2*t[0..15] + sum a[i]^2 * 2^(64 i)      (t < 2^511)
+KH_HD void kh_double_add_squares(uint32_t r[16], const uint32_t t[16], const uint32_t a[8]) {
+  uint32_t d[16];
+  d[0] = t[0] << 1;
+#pragma unroll
+  for (int i = 1; i < 16; i++) d[i] = (t[i] << 1) | (t[i - 1] >> 31);
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\tmadc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\tmadc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\tmadc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\tmadc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\tmadc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\tmadc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\tmadc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\tmadc.hi.u32 %15, %23, %23, %15;\n\t"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]),
+        "+r"(d[8]), "+r"(d[9]), "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t p = (uint64_t)a[i] * a[i];
+    uint64_t s = (uint64_t)d[2 * i] + (uint32_t)p + c;
+    d[2 * i] = (uint32_t)s; c = s >> 32;
+    s = (uint64_t)d[2 * i + 1] + (p >> 32) + c;
+    d[2 * i + 1] = (uint32_t)s; c = s >> 32;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 16; i++) r[i] = d[i];
+}
 // r[0..15] = e[0..15] + (o[0..14] << 32)   (final combination of the even/odd accumulators)
 KH_HD void kh_combine_eo(uint32_t r[16], const uint32_t e[17], const uint32_t o[17]) {
   r[0] = e[0];
@@ -248,7 +317,37 @@ KH_HD void fe_mul(fe &r, const fe &a, const fe &b) {
   fe_mul_wide(w, a, b);
   fe_reduce_wide(r, w);
 }
-KH_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+// a^2 with 36 instead of 64 wide multiplies: off-diagonal products once (even/odd columns as in
+// fe_mul_wide), doubled, plus the eight squares.  Used where the FMA-heavy pipe is the bottleneck
+// (xpoint / BSGS walks: ncu shows it 71 % busy with IMAD.WIDE).
+KH_HD void fe_sqr_wide(uint32_t r[16], const fe &a) {
+  uint32_t e[17], o[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
+  const uint32_t *v = a.v;
+  // row i: a_i * a_j for j > i ; column i+j odd -> o[i+j-1], even -> e[i+j]
+  { const uint32_t x[4] = {v[0], v[0], v[0], v[0]}, y[4] = {v[1], v[3], v[5], v[7]}; kh_mad_chain<4>(o + 0, x, y); }
+  { const uint32_t x[3] = {v[0], v[0], v[0]}, y[3] = {v[2], v[4], v[6]}; kh_mad_chain<3>(e + 2, x, y); }
+  { const uint32_t x[3] = {v[1], v[1], v[1]}, y[3] = {v[2], v[4], v[6]}; kh_mad_chain<3>(o + 2, x, y); }
+  { const uint32_t x[3] = {v[1], v[1], v[1]}, y[3] = {v[3], v[5], v[7]}; kh_mad_chain<3>(e + 4, x, y); }
+  { const uint32_t x[3] = {v[2], v[2], v[2]}, y[3] = {v[3], v[5], v[7]}; kh_mad_chain<3>(o + 4, x, y); }
+  { const uint32_t x[2] = {v[2], v[2]}, y[2] = {v[4], v[6]}; kh_mad_chain<2>(e + 6, x, y); }
+  { const uint32_t x[2] = {v[3], v[3]}, y[2] = {v[4], v[6]}; kh_mad_chain<2>(o + 6, x, y); }
+  { const uint32_t x[2] = {v[3], v[3]}, y[2] = {v[5], v[7]}; kh_mad_chain<2>(e + 8, x, y); }
+  { const uint32_t x[2] = {v[4], v[4]}, y[2] = {v[5], v[7]}; kh_mad_chain<2>(o + 8, x, y); }
+  { const uint32_t x[1] = {v[4]}, y[1] = {v[6]}; kh_mad_chain<1>(e + 10, x, y); }
+  { const uint32_t x[1] = {v[5]}, y[1] = {v[6]}; kh_mad_chain<1>(o + 10, x, y); }
+  { const uint32_t x[1] = {v[5]}, y[1] = {v[7]}; kh_mad_chain<1>(e + 12, x, y); }
+  { const uint32_t x[1] = {v[6]}, y[1] = {v[7]}; kh_mad_chain<1>(o + 12, x, y); }
+  uint32_t t[16];
+  kh_combine_eo(t, e, o);
+  kh_double_add_squares(r, t, v);
+}
+KH_HD void fe_sqr(fe &r, const fe &a) {
+  uint32_t w[16];
+  fe_sqr_wide(w, a);
+  fe_reduce_wide(r, w);
+}
 
 // Out-of-line multiply: the hash-heavy scan kernels are instruction-fetch bound (ncu: stall no_instruction,
 // GPC instruction-cache requests at >90 % of peak), so their EC loop calls ONE shared copy of the multiplier

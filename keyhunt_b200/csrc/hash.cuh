@@ -51,14 +51,15 @@ KH_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
 
 // ---- pipe balancing ---------------------------------------------------------------------------------
-// SHA-256 / RIPEMD-160 are pure ALU-pipe code (SHF, LOP3, IADD3).  kh_addf(a, b) computes a + b as IMAD
-// a*1+b with the 1 taken from constant memory (so ptxas cannot fold it back into an IADD), which moves the
-// addition onto the FMA-heavy pipe.  Measured on B200 (kh_hash_peak, tools_hashpeak.py): SHA-256 alone gains
-// 15 % (13.9 -> 16.0 G compressions/s) but RIPEMD-160 loses 37 % (28.3 -> 17.7 G/s, it has more adds than
-// logic ops, so the IMADs become the bottleneck) and the fused scan kernels lose 2-4 % (they already keep the
-// FMA-heavy pipe 50-70 % busy with IMAD.WIDE field multiplications).  Hence OFF by default; kept for A/B.
+// SHA-256 / RIPEMD-160 are pure ALU-pipe code (SHF, LOP3, IADD3) and the hash-heavy scan kernels run the
+// ALU pipe at 82-87 % of peak while the FMA-heavy pipe is ~25 % busy (ncu, profiles/r01_v3_*).  kh_addf(a, b)
+// computes a + b as IMAD a*1+b with the 1 taken from constant memory (so ptxas cannot fold it back into an
+// IADD), which moves the addition onto the FMA-heavy pipe.  It is applied to the SHA-256 rounds and schedule
+// only: measured on B200 (kh_hash_peak) SHA-256 alone gains 15 % (13.9 -> 16.0 G compressions/s), whereas
+// RIPEMD-160 (more adds than logic ops) LOSES 37 % when its adds are moved, so it keeps plain adds.
+// Fused kernels: comp +3 %, uncomp +6 %, both +4.5 %.
 #ifndef KH_FMA_ADDS
-#define KH_FMA_ADDS 0
+#define KH_FMA_ADDS 1
 #endif
 #if defined(__CUDACC__)
 static __constant__ uint32_t kh_c_one = 1u;
@@ -92,10 +93,10 @@ KH_HD uint32_t kh_addf(uint32_t a, uint32_t b) {
 #define KH_RMD_F2(x, y, z) (((x) | ~(y)) ^ (z))
 #define KH_RMD_F3(x, y, z) (((x) & (z)) | ((y) & ~(z)))
 #define KH_RMD_F4(x, y, z) ((x) ^ ((y) | ~(z)))
-#define KH_RMD_STEP(F, a, b, c, d, e, xv, k, s)                         \
-  {                                                                     \
-    a = kh_addf(rotl32(kh_addf(kh_addf(a, F(b, c, d)), (xv) + (k)), s), e); \
-    c = rotl32(c, 10);                                                  \
+#define KH_RMD_STEP(F, a, b, c, d, e, xv, k, s)              \
+  {                                                          \
+    a = rotl32(a + F(b, c, d) + (xv) + (k), s) + e;          \
+    c = rotl32(c, 10);                                       \
   }
 
 #define KH_SHA_K_LIST                                                                               \

@@ -140,7 +140,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
           if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
           fe_mul_sel<OL>(s, dy, dinv);
-          fe_mul_sel<OL>(s2, s, s);
+          if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
           fe_sub(x3, s2, px);
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
