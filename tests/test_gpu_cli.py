@@ -1,0 +1,122 @@
+"""GPU: the drop-in command-line driver (keyhunt_b200/keyhunt-b200) against the UNMODIFIED reference binary
+(oracle/_ref/keyhunt, CPU) run side by side on the same command lines: identical KEYFOUNDKEYFOUND.txt records
+and identical `-S` BSGS table files."""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+from _oracle import REF_BIN
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CLI = os.path.join(ROOT, "keyhunt_b200", "keyhunt-b200")
+SCANS = {c["name"]: c for c in json.load(open(os.path.join(GOLD, "scans.json")))}
+
+
+def run(exe, args, cwd):
+    r = subprocess.run([exe] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    return r.returncode, r.stdout
+
+
+def records(cwd, per):
+    """KEYFOUNDKEYFOUND.txt as a sorted list of `per`-line records (hit order varies with threads)"""
+    fn = os.path.join(cwd, "KEYFOUNDKEYFOUND.txt")
+    if not os.path.exists(fn):
+        return []
+    lines = open(fn).read().splitlines()
+    return sorted("|".join(lines[i:i + per]) for i in range(0, len(lines), per))
+
+
+@pytest.fixture()
+def dirs():
+    a, b = tempfile.mkdtemp(prefix="khcli_gpu_"), tempfile.mkdtemp(prefix="khcli_ref_")
+    yield a, b
+    shutil.rmtree(a, ignore_errors=True)
+    shutil.rmtree(b, ignore_errors=True)
+
+
+CASES = [
+    ("address_compress", ["-m", "address", "-f", GOLD + "/1to32.txt", "-r", "1:FFFFFF", "-l", "compress", "-n", "0x100000"], 4),
+    ("rmd160_both", ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:3FFFFF", "-l", "both", "-n", "0x100000"], 4),
+    ("address_eth", ["-m", "address", "-c", "eth", "-f", GOLD + "/1to32.eth", "-r", "1:FFFFFF", "-n", "0x100000"], 2),
+    ("xpoint", ["-m", "xpoint", "-f", GOLD + "/substracted40.txt", "-r", "8000000000:8003000000", "-n", "0x100000"], 4),
+    ("stride", ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:FFFFF", "-l", "compress", "-n", "0x100000", "-I", "3"], 4),
+]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/keyhunt not built")
+@pytest.mark.parametrize("name,args,per", CASES)
+def test_cli_output_identical_to_reference(dirs, name, args, per):
+    g, r = dirs
+    rc_g, out_g = run(CLI, args + ["-q", "-t", "1"], g)
+    rc_r, out_r = run(REF_BIN, args + ["-q", "-s", "0", "-t", str(os.cpu_count() or 4)], r)
+    assert rc_g == 0 and "End" in out_g, out_g[-2000:]
+    assert rc_r == 0 and "End" in out_r, out_r[-2000:]
+    rec_g, rec_r = records(g, per), records(r, per)
+    assert rec_g == rec_r
+    assert len(rec_g) >= (2 if name != "stride" else 1)
+
+
+def test_cli_planted_uncompressed_and_opposite_parity(dirs):
+    g, _ = dirs
+    for name, flag in (("planted_uncompress", "uncompress"), ("planted_opposite_parity", "compress")):
+        fn = os.path.join(g, name + ".rmd")
+        open(fn, "w").write("\n".join(SCANS[name]["targets"]) + "\n")
+        if os.path.exists(os.path.join(g, "KEYFOUNDKEYFOUND.txt")):
+            os.remove(os.path.join(g, "KEYFOUNDKEYFOUND.txt"))
+        rc, out = run(CLI, ["-m", "rmd160", "-f", fn, "-r", "2000000000000000:2000000000400000", "-l", flag, "-n", "0x100000", "-q"], g)
+        assert rc == 0, out[-2000:]
+        keys = sorted(int(rec.split("|")[0].split(":")[1], 16) for rec in records(g, 4))
+        assert keys == sorted(int(k, 16) for k in SCANS[name]["keys"])
+
+
+def test_cli_c1_full_sweep_checksum(dirs):
+    """BASELINE config 1 end to end: the canonicalised KEYFOUNDKEYFOUND.txt of the full -r 1:FFFFFFFF sweep has the
+    SHA-256 the reference run produced (cb75e1c2...c6ffbb)"""
+    g, _ = dirs
+    rc, out = run(CLI, ["-m", "address", "-f", GOLD + "/1to32.txt", "-r", "1:FFFFFFFF", "-l", "compress", "-q"], g)
+    assert rc == 0 and "End" in out, out[-2000:]
+    recs = records(g, 4)
+    assert len(recs) == 32
+    digest = hashlib.sha256(("\n".join(recs) + "\n").encode()).hexdigest()
+    assert digest == "cb75e1c290cfb3c669936eebbcdfb7ef1f192ca578edcbcd03e8371471c6ffbb"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/keyhunt not built")
+def test_cli_bsgs_files_and_keys_identical_to_reference(dirs):
+    g, r = dirs
+    pubs = [l.strip() for l in open(os.path.join(GOLD, "bsgs_pubkeys.txt")) if l.strip()]
+    for d in (g, r):
+        open(os.path.join(d, "p.txt"), "w").write("\n".join(pubs) + "\n")
+    args = ["-m", "bsgs", "-f", "p.txt", "-n", "0x400000", "-k", "2", "-r", "100000:10000000000", "-S", "-q"]
+    rc_g, out_g = run(CLI, args + ["-t", "1"], g)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", str(os.cpu_count() or 4)], r)
+    assert "All points were found" in out_g, out_g[-2000:]
+    assert "All points were found" in out_r, out_r[-2000:]
+    assert rc_g == rc_r == 1                      # sic: success exits with EXIT_FAILURE (keyhunt.cpp:4855-4858)
+    assert records(g, 2) == records(r, 2) and len(records(g, 2)) == len(pubs)
+    files = sorted(f for f in os.listdir(r) if f.startswith("keyhunt_bsgs_"))
+    assert files == sorted(f for f in os.listdir(g) if f.startswith("keyhunt_bsgs_")) and len(files) == 4
+    for fn in files:
+        a, b = open(os.path.join(g, fn), "rb").read(), open(os.path.join(r, fn), "rb").read()
+        assert len(a) == len(b), fn
+        if fn.endswith(".blm"):
+            rec = len(a) // 256
+            for s in range(256):
+                ra, rb = bytearray(a[s * rec:(s + 1) * rec]), bytearray(b[s * rec:(s + 1) * rec])
+                ra[64:72] = rb[64:72] = b"\0" * 8          # struct bloom.bf is a heap pointer of the writing process
+                assert ra == rb, (fn, s)
+        else:
+            body = lambda x: sorted(x[i:i + 16] for i in range(0, len(x) - 32, 16))   # reference sort is not stable (ties)
+            assert body(a) == body(b)
+            assert a[-32:] == hashlib.sha256(a[:-32]).digest()
+    # second run loads the files instead of rebuilding and still finds the keys
+    os.remove(os.path.join(g, "KEYFOUNDKEYFOUND.txt"))
+    rc, out = run(CLI, args + ["-t", "1"], g)
+    assert "tables loaded from files" in out and "All points were found" in out
