@@ -78,6 +78,37 @@ KH_HD void bloom_set(const BloomDev &bl, uint32_t shard, uint64_t a, uint64_t b)
   }
 }
 
+// Two membership tests at once.  The first KH_BLOOM_PAR bit positions of BOTH keys are loaded before any
+// of them is examined (2*KH_BLOOM_PAR independent loads in flight instead of one dependent load at a time);
+// the rare survivors finish in a joint loop.  The result is the same AND over all `hashes` bits as
+// bloom_check's early-exit loop (bloom.cpp:189-212), only the evaluation order differs.
+#ifndef KH_BLOOM_PAR
+#define KH_BLOOM_PAR 2
+#endif
+KH_HD void bloom_test_pair(const BloomDev &bl, uint32_t shardA, uint64_t aA, uint64_t bA, uint32_t shardB, uint64_t aB,
+                           uint64_t bB, bool &okA, bool &okB) {
+  const uint8_t *bfA = bl.bf + (uint64_t)shardA * bl.stride;
+  const uint8_t *bfB = bl.bf + (uint64_t)shardB * bl.stride;
+  uint64_t xA = aA, xB = aB;
+  uint8_t vA[KH_BLOOM_PAR], vB[KH_BLOOM_PAR];
+  uint32_t sA[KH_BLOOM_PAR], sB[KH_BLOOM_PAR];
+#pragma unroll
+  for (int k = 0; k < KH_BLOOM_PAR; k++) {
+    const uint64_t rA = bloom_mod(xA, bl.bits, bl.magic), rB = bloom_mod(xB, bl.bits, bl.magic);
+    vA[k] = okA ? kh_ld_u8(bfA + (rA >> 3)) : (uint8_t)0;
+    vB[k] = okB ? kh_ld_u8(bfB + (rB >> 3)) : (uint8_t)0;
+    sA[k] = (uint32_t)(rA & 7); sB[k] = (uint32_t)(rB & 7);
+    xA += bA; xB += bB;
+  }
+#pragma unroll
+  for (int k = 0; k < KH_BLOOM_PAR; k++) { okA = okA && ((vA[k] >> sA[k]) & 1); okB = okB && ((vB[k] >> sB[k]) & 1); }
+#pragma unroll 1
+  for (uint32_t i = KH_BLOOM_PAR; i < bl.hashes && (okA || okB); i++) {
+    if (okA) { const uint64_t r = bloom_mod(xA, bl.bits, bl.magic); okA = (kh_ld_u8(bfA + (r >> 3)) >> (r & 7)) & 1; xA += bA; }
+    if (okB) { const uint64_t r = bloom_mod(xB, bl.bits, bl.magic); okB = (kh_ld_u8(bfB + (r >> 3)) >> (r & 7)) & 1; xB += bB; }
+  }
+}
+
 KH_HD bool bloom_check20(const BloomDev &bl, const uint32_t w[5]) {
   uint64_t a = xxh64_20(w, KH_BLOOM_SEED);
   uint64_t b = xxh64_20(w, a);

@@ -63,6 +63,7 @@ struct ScanEmit {
 #define KH_OUTLINE_MUL 1
 #endif
   static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT);
+  static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT);
   const ScanTargets &tg;
   KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
 
@@ -71,6 +72,18 @@ struct ScanEmit {
       if (table_contains(tg.table, tg.n, h))           // keyhunt.cpp:3623
         sink_push(tg.sink, batch, idx, kind, h);
     }
+  }
+  // xpoint: both points of a +-e pair, bloom probes of the two overlapped (keyhunt.cpp:3810-3821 twice)
+  KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
+    uint32_t ha[5], hb[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ha[i] = bswap32(xa.v[7 - i]); hb[i] = bswap32(xb.v[7 - i]); }
+    const uint64_t aA = xxh64_20(ha, KH_BLOOM_SEED), aB = xxh64_20(hb, KH_BLOOM_SEED);
+    const uint64_t bA = xxh64_20(ha, aA), bB = xxh64_20(hb, aB);
+    bool okA = true, okB = true;
+    bloom_test_pair(tg.bloom, 0, aA, bA, 0, aB, bB, okA, okB);
+    if (okA && table_contains(tg.table, tg.n, ha)) sink_push(tg.sink, batch, ia, KH_KIND_XPOINT, ha);
+    if (okB && table_contains(tg.table, tg.n, hb)) sink_push(tg.sink, batch, ib, KH_KIND_XPOINT, hb);
   }
   KH_HDM void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
     uint32_t h[5];
@@ -113,6 +126,12 @@ struct BsgsTables {
 struct BabyEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
+  static constexpr bool PAIRS = true;
+  KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
+    const fe dummy = xa;
+    point(xa, dummy, batch, ia);
+    point(xb, dummy, batch, ib);
+  }
   const BsgsTables &bt;
   KH_HDM explicit BabyEmit(const BsgsTables &b) : bt(b) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
@@ -156,6 +175,23 @@ struct GiantParams {
 struct GiantEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
+  static constexpr bool PAIRS = true;
+  KH_HDM void push(uint64_t batch, uint32_t idx) {
+    uint32_t slot = kh_atomic_inc(gp.count);
+    if (slot < gp.cap) { GiantCand c; c.batch = batch; c.idx = idx; c.pad = 0; gp.cands[slot] = c; }
+  }
+  // two giant steps at once: 2 x 2 XXH64 chains interleaved, tier-1 probes of both in flight together
+  KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
+    uint32_t wa[8], wb[8];
+    fe_to_le_words(wa, xa);
+    fe_to_le_words(wb, xb);
+    const uint64_t aA = xxh64_32(wa, KH_BLOOM_SEED), aB = xxh64_32(wb, KH_BLOOM_SEED);
+    const uint64_t bA = xxh64_32(wa, aA), bB = xxh64_32(wb, aB);
+    bool okA = (batch * KH_GRP + ia) < gp.n_steps, okB = (batch * KH_GRP + ib) < gp.n_steps;
+    bloom_test_pair(gp.tier1, xa.v[7] >> 24, aA, bA, xb.v[7] >> 24, aB, bB, okA, okB);
+    if (okA) push(batch, ia);
+    if (okB) push(batch, ib);
+  }
   const GiantParams &gp;
   KH_HDM explicit GiantEmit(const GiantParams &g) : gp(g) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {

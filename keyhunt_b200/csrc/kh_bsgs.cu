@@ -18,6 +18,9 @@
 using namespace kh;
 
 #define KH_BLOCK 256
+#ifndef KH_GIANT_MINBLOCKS
+#define KH_GIANT_MINBLOCKS 2
+#endif
 
 __device__ __forceinline__ void kh_stage_table_b(uint32_t *smem, const uint32_t *gtab) {
   const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(KH_BLOCK, 2) kh_baby_kernel(WalkParams wp, Bsg
   walk_batches(wp, kh_smem_tab, t, emit);
 }
 
-__global__ void __launch_bounds__(KH_BLOCK, 2) kh_giant_kernel(WalkParams wp, GiantParams gp) {
+__global__ void __launch_bounds__(KH_BLOCK, KH_GIANT_MINBLOCKS) kh_giant_kernel(WalkParams wp, GiantParams gp) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table_b(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -127,6 +127,22 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       } else {
         dinv = inv;
       }
+      if (Emit::PAIRS && e != 0 && e != KH_HALF) {
+        // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
+        // emitter, the bloom probes of both points in flight at the same time (memory-level parallelism)
+        fe dyp, dym, sp, sm, xp, xm, c;
+        fe_sub(dyp, gy, py);
+        fe_add(dym, gy, py);
+        fe_mul(sp, dyp, dinv);
+        fe_mul(sm, dym, dinv);
+        fe_sqr(xp, sp);
+        fe_sqr(xm, sm);
+        fe_add(c, px, gx);
+        fe_sub(xp, xp, c);
+        fe_sub(xm, xm, c);
+        emit.pair(xp, (uint32_t)(KH_HALF + e), xm, (uint32_t)(KH_HALF - e), batch);
+        continue;
+      }
 #pragma unroll 1
       for (int sgn = 0; sgn < 2; sgn++) {
         if (e == KH_HALF && sgn == 0) continue;        // +512*S belongs to the next batch (pts[0] there)

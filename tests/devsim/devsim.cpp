@@ -112,6 +112,8 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
 struct DumpEmit {
   static constexpr bool NEED_Y = true;
   static constexpr bool OUTLINE_MUL = false;
+  static constexpr bool PAIRS = false;
+  void pair(const fe &, uint32_t, const fe &, uint32_t, uint64_t) {}
   uint8_t *out;
   void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
     uint8_t *p = out + (batch * KH_GRP + idx) * 64;
