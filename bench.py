@@ -95,7 +95,7 @@ def make_targets(kh, K, wl, seed, n_points_total):
         recs.append(r)
     while len(recs) < w["n_targets"]:
         recs.append(rnd.randbytes(20))
-    rnd.shuffle(recs)
+    recs.sort()      # the reference's boundary hands over the sorted addressTable (_sort, keyhunt.cpp:1361)
     return b"".join(recs), planted
 
 

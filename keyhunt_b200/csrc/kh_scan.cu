@@ -16,6 +16,9 @@
 using namespace kh;
 
 #define KH_BLOCK 256
+#ifndef KH_SCAN_MINBLOCKS
+#define KH_SCAN_MINBLOCKS 2
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
@@ -44,7 +47,7 @@ __device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *g
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(KH_BLOCK, 2) kh_scan_kernel(WalkParams wp, ScanTargets tg) {
+__global__ void __launch_bounds__(KH_BLOCK, KH_SCAN_MINBLOCKS) kh_scan_kernel(WalkParams wp, ScanTargets tg) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,7 +280,10 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
   // sorted table (_sort keyhunt.cpp:4307: ascending memcmp order)
   std::vector<uint64_t> order(n);
   std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return memcmp(records20 + 20 * a, records20 + 20 * b, 20) < 0; });
+  bool sorted = true;   // the reference hands over an already sorted addressTable: skip the sort then
+  for (uint64_t i = 1; i < n && sorted; i++) sorted = memcmp(records20 + 20 * (i - 1), records20 + 20 * i, 20) <= 0;
+  if (!sorted)
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return memcmp(records20 + 20 * a, records20 + 20 * b, 20) < 0; });
   c->h_table20.resize(20 * n);
   std::vector<uint32_t> packed(5 * n);
   for (uint64_t i = 0; i < n; i++) {

@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B the library variants in gpurun_variants/ with the throughput probe
+# A/B the library variants in gpurun_variants/ with the throughput probe; TPS = threads per SM list
 cd "${GRAFT_REPO_ROOT:-.}"
 for v in gpurun_variants/libkh_*.so; do
-  echo "=== $v"
-  KH_B200_LIB=$PWD/$v python tools_perf_probe.py 512 2>&1 | grep "tp=" | awk '{print $2, $7}'
+  for tp in ${TPS:-512}; do
+    echo "=== $v tp=$tp"
+    KH_B200_LIB=$PWD/$v python tools_perf_probe.py $tp 2>&1 | grep "tp=" | awk '{print $2, $7}'
+  done
 done
