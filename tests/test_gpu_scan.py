@@ -115,3 +115,53 @@ def test_multi_launch_and_tail(kh, oracle):
     finally:
         kh.set_option("steps_per_launch", 16)
         kh.set_option("threads_per_sm", 512)
+
+
+def test_empty_and_duplicate_targets(kh, oracle):
+    # empty target set: bloom of 10,000 entries with no bit set -> no hits, no errors (N = 0 after an all-invalid file)
+    kh.set_targets(K.MODE_XPOINT, b"")
+    d, bits = kh.get_bloom()
+    assert d.entries == 10000 and not any(bits)
+    kh.scan(12345, 4096)
+    assert kh.poll_hits() == []
+    # duplicate records: the table keeps both, a key is still reported once per matching hash
+    x, _ = oracle.pubkey(0x5000 + 7)
+    rec = be32(x)[:20]
+    kh.set_targets(K.MODE_XPOINT, rec * 3 + bytes(20))
+    assert kh.get_table() == bytes(20) + rec * 3
+    kh.scan(0x5000, 1024)
+    hits = kh.poll_hits()
+    assert [(h.index, h.key) for h in hits] == [(7, 0x5007)]
+
+
+def test_hit_buffer_overflow_is_reported(kh, oracle):
+    """every point of the range is a target: more hits than the device hit buffer holds -> KH_EOVERFLOW (loud, not silent)"""
+    start, n = 0x7000, 2048
+    raw = b"".join(oracle.batch_points(start + b * 1024, 1, False) for b in range(n // 1024))
+    recs = b"".join(raw[64 * i:64 * i + 20] for i in range(n))
+    kh.set_targets(K.MODE_XPOINT, recs)
+    kh.scan(start, n)
+    assert sorted(h.index for h in kh.poll_hits()) == list(range(n))      # default capacity holds them all
+    kh.set_option("hit_capacity", 16)
+    try:
+        kh.scan(start, n)
+        with pytest.raises(K.KhError) as ei:
+            kh.poll_hits()
+        assert ei.value.code == -5
+    finally:
+        kh.set_option("hit_capacity", 1 << 16)
+        kh.poll_hits()
+
+
+def test_bad_arguments(kh):
+    kh.set_targets(K.MODE_XPOINT, bytes(20))
+    for bad in (0, 1000, 1025):
+        with pytest.raises(K.KhError) as ei:
+            kh.scan(1, bad)
+        assert ei.value.code == -2
+    with pytest.raises(K.KhError):
+        kh.scan(1, 1024, stride=0)
+    with pytest.raises(K.KhError):
+        kh.bsgs_build(1 << 21, 1)      # not an even power of two
+    with pytest.raises(K.KhError):
+        kh.set_targets(K.MODE_BSGS, bytes(20))
