@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench_bsgs.py — C4 (BASELINE.json configs[3]): `-m bsgs -k 512`, n = 2^44, one public key in a 2^64-wide
 range, bP table + 3-tier bloom resident in HBM.  Same JSON-line contract as bench.py (which stays on the
-headline C2 workload); a step is one sweep of 2^13 windows (2^26 giant steps, 2^58 keys).
+headline C2 workload); a step is one sweep of 2^15 windows (2^28 giant steps, 2^60 keys).
 
   python bench_bsgs.py [--k 512] [--steps 16] [--warmup 3] [--cpu-k 16] [--no-cpu-baseline]
 
@@ -88,7 +88,7 @@ def main():
     build = {"wall_s": build_wall, "baby_walk_ms": st["walk_ms"], "sort_ms": st["aux_ms"], "baby_steps_per_s": d.m / (st["walk_ms"] * 1e-3),
              "tier1_GB": d.tier[0].bytes * 256 / 1e9, "m": d.m, "m2": d.m2, "m3": d.m3, "launches": st["walk_launches"] + st["other_launches"]}
     win = 2 * N44                      # keys per window
-    W = 1 << 13                        # windows per step
+    W = 1 << 15                        # windows per step
     start = 1 << 64
     # planted key (found in window 37) — time to find from the range start
     rnd = random.Random(4)
@@ -136,7 +136,7 @@ def main():
         "metric": "Pkeys/s (c4 bsgs -k %d)" % args.k, "value": keys_s / 1e15, "unit": "Pkeys/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "C4 bsgs -k %d, n=2^44 (m=2^%d), 1 public key, range [2^64, 2^65), step = 2^13 windows = 2^26 giant steps"
+        "config": {"workload": "C4 bsgs -k %d, n=2^44 (m=2^%d), 1 public key, range [2^64, 2^65), step = 2^15 windows = 2^28 giant steps"
                                % (args.k, d.m.bit_length() - 1), "gpu": info["name"],
                    "l2_note": "tier-1 bloom (%.1f GB) is far larger than L2; every probe is a random HBM sector" % build["tier1_GB"]},
         "clocks": clk, "build": build,
