@@ -290,6 +290,8 @@ def main():
         log("[bench] warm-up raised to 3 (timing rules)")
         args.warmup = 3
 
+    # stdout must carry exactly one JSON line: NCCL's version/debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import keyhunt_b200 as K
     dist = None
