@@ -432,9 +432,13 @@ def main():
                 "h2d_bytes_per_step": len(records) + 64, "d2h_bytes_per_step": 8 + 160 * max(1, len(e2e_hits)) // max(1, e2e_steps),
                 "steps": e2e_steps, "launches": st_e2e["walk_launches"] + st_e2e["other_launches"]},
         "gpu_launches": int(launches.item()),
+        "displayed_keys_value": value * w["disp"],   # the reference multiplies by 2 for -l compress (keyhunt.cpp:2889-2891)
         "wall_ms_per_step": wall_ms_max / Ksteps,
         "hits": {"found": len(got_keys), "all_planted_found_and_nothing_else": ok},
-        "roofline": {"bound": "int", "achieved": achieved, "peak": peak, "unit": "Tiop/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "int", "achieved": achieved, "peak": peak, "unit": "Tiop/s", "frac": achieved / peak,
+                     # DRAM bytes per launch: ncu --set full measured 39.23 GB for a 1.2416 G-point launch of this kernel
+                     # (profiles/r01_v1_scan_both_ncu_full_summary.txt) = 31.6 B/point = the algorithmic scratch write+read
+                     "traffic": 31.6 * pts_per_launch, "traffic_unit": "bytes of DRAM read+write per launch (ncu-measured 31.6 B/point x points per launch)",
                      "kernel": "kh_scan_kernel", "ops_per_point": w["ops"], "launch_ms": launch_ms,
                      "peak_source": "measured live: kh_int_peak LOP3+IMAD dual-pipe rate; ALU pipe alone %.2f, IMAD %.2f, IMAD.WIDE %.2f Tiop/s"
                                     % (peaks["lop3"] / 1e12, peaks["imad"] / 1e12, peaks["imad_wide"] / 1e12),

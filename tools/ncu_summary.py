@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Compact summary of an .ncu-rep (raw page): python tools_ncu_summary.py report.ncu-rep [out.txt]"""
+"""Compact summary of an .ncu-rep (raw page): python tools/ncu_summary.py report.ncu-rep [out.txt]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""One short scan of a given kind (for ncu section captures): python tools_prof_kernel.py comp|both|xpoint|uncomp|eth [log2 points]"""
+"""One short scan of a given kind (for ncu section captures): python tools/prof_kernel.py comp|both|xpoint|uncomp|eth [log2 points]"""
 import random, sys
 sys.path.insert(0, ".")
 import keyhunt_b200 as K
