@@ -72,3 +72,42 @@ def test_bsgs_reference_fixture_puzzles(kh, oracle):
             0x7d4fe747, 0xb862a62e]
     for key in keys:
         assert kh.bsgs_search(oracle.pubkey(key), 0x100000, 0x10000000000) == key
+
+
+def test_c4_full_size_properties(kh, oracle):
+    """BASELINE config 4 at its real size (bsgs -k 512, n = 2^44: m = 2^31 baby points, 7.7 GB tier-1 bloom) through
+    size-independent properties: the reference's sizes, membership of sampled baby points in every tier they belong
+    to, bP table = sorted permutation with the right keys, planted keys found in the first / a middle / the last window."""
+    kh.bsgs_build(1 << 44, 512)
+    d = kh.bsgs_describe()
+    assert (d.m, d.m2, d.m3, d.aux) == (1 << 31, 1 << 26, 1 << 21, 8192)
+    assert [d.tier[i].bytes for i in range(3)] == [30151987, 942250, 35944]          # SURVEY App. A.4 (reference-probed)
+    rnd = random.Random(44)
+    shards = {}
+
+    def member(tier, x):
+        xb = x.to_bytes(32, "big")
+        if (tier, xb[0]) not in shards:
+            shards[(tier, xb[0])] = kh.bsgs_export(tier, xb[0])
+        bf, desc = shards[(tier, xb[0])], d.tier[tier - 1]
+        a = oracle.xxh64(xb, 0x59f2815b16f81798)
+        b = oracle.xxh64(xb, a)
+        return all((bf[(((a + b * i) & (2**64 - 1)) % desc.bits) >> 3] >> ((((a + b * i) & (2**64 - 1)) % desc.bits) & 7)) & 1
+                   for i in range(desc.hashes))
+
+    for tier, top in ((3, d.m3), (2, d.m2), (1, d.m)):
+        assert all(member(tier, oracle.pubkey(j)[0]) for j in [1, top] + [rnd.randrange(1, top + 1) for _ in range(6)])
+    shards.clear()
+    assert not member(3, oracle.pubkey(d.m3 + 1)[0]) or not member(3, oracle.pubkey(d.m3 + 2)[0])   # beyond the tier: not inserted
+    shards.clear()
+    tab = kh.bsgs_export(0)
+    ents = [(tab[i:i + 6], int.from_bytes(tab[i + 8:i + 16], "little")) for i in range(0, len(tab), 16)]
+    assert all(ents[i] <= ents[i + 1] for i in range(len(ents) - 1))
+    assert sorted(e[1] for e in ents) == list(range(d.m3))
+    for i in rnd.sample(range(d.m3), 12):
+        assert ents[i][0] == oracle.pubkey(ents[i][1] + 1)[0].to_bytes(32, "big")[16:22]
+    lo, hi = 1 << 64, 1 << 65
+    for key in (lo + 5, lo + 37 * (1 << 45) + rnd.randrange(1 << 45), hi - 12345):
+        assert kh.bsgs_search(oracle.pubkey(key), lo, hi) == key
+    st = kh.stats()
+    assert st["tier1_positives"] > 0
