@@ -383,6 +383,79 @@ static bool bsgs_load(kh_ctx *c, const kh_bsgs_desc &d) {   // all four files mu
   return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// scan-mode target cache `data_<first 4 bytes of sha256(target file)>.dat` (writeFileIfNeeded keyhunt.cpp:7756,
+// readFileAddress :7043-7206): 32 B sha256(bf) | struct bloom (112 B) | bf | 32 B sha256(table) | u64 size | table
+// ---------------------------------------------------------------------------------------------------
+static bool sha256_of_file(const char *fn, uint8_t out[32]) {
+  FILE *f = fopen(fn, "rb");
+  if (!f) return false;
+  std::vector<uint8_t> buf;
+  uint8_t tmp[65536];
+  size_t n;
+  while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+  fclose(f);
+  sha256_host(buf.data(), buf.size(), out);
+  return true;
+}
+static std::string dat_name(const char *targets) {
+  uint8_t sum[32];
+  if (!sha256_of_file(targets, sum)) { fprintf(stderr, "[E] sha256_file error\n"); exit(EXIT_FAILURE); }
+  return "data_" + hex_of(sum, 4) + ".dat";
+}
+static bool dat_read(const std::string &fn, kh_bloom_desc &d, std::vector<uint8_t> &bf, std::vector<uint8_t> &table) {
+  FILE *f = fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  printf("[+] Reading file %s\n", fn.c_str());
+  uint8_t bsum[32], dsum[32], hdr[112], sum[32];
+  uint64_t size = 0;
+  bool ok = fread(bsum, 1, 32, f) == 32 && fread(hdr, 1, 112, f) == 112;
+  if (ok) {
+    memcpy(&d.entries, hdr, 8); memcpy(&d.bits, hdr + 8, 8); memcpy(&d.bytes, hdr + 16, 8);
+    d.hashes = hdr[24]; d.pad = 0;
+    ok = d.bytes < (1ULL << 40) && d.bits && d.hashes;
+  }
+  if (ok) { bf.resize(d.bytes); ok = fread(bf.data(), 1, d.bytes, f) == d.bytes; }
+  if (ok) ok = fread(dsum, 1, 32, f) == 32 && fread(&size, 1, 8, f) == 8 && size % 20 == 0 && size < (1ULL << 40);
+  if (ok) { table.resize(size); ok = size == 0 || fread(table.data(), 1, size, f) == size; }
+  fclose(f);
+  if (!ok) { fprintf(stderr, "[E] Error reading file %s\n", fn.c_str()); return false; }
+  if (!FLAGSKIPCHECKSUM) {
+    sha256_host(bf.data(), bf.size(), sum);
+    if (memcmp(sum, bsum, 32)) { fprintf(stderr, "[E] Error checksum mismatch (bloom) in %s\n", fn.c_str()); return false; }
+    sha256_host(table.data(), table.size(), sum);
+    if (memcmp(sum, dsum, 32)) { fprintf(stderr, "[E] Error checksum mismatch (data) in %s\n", fn.c_str()); return false; }
+  }
+  printf("[+] Bloom filter for %" PRIu64 " elements.\n", d.entries);
+  return true;
+}
+static void dat_write(const std::string &fn, kh_ctx *c) {
+  kh_bloom_desc d;
+  if (kh_get_bloom(c, &d, NULL, 0) != KH_OK) die("[E] %s", kh_last_error(c));
+  std::vector<uint8_t> bf(d.bytes);
+  uint64_t n = 0;
+  if (kh_get_bloom(c, &d, bf.data(), bf.size()) != KH_OK || kh_get_table(c, NULL, 0, &n) != KH_OK) die("[E] %s", kh_last_error(c));
+  std::vector<uint8_t> table(n * 20 + 1);
+  if (kh_get_table(c, table.data(), n, &n) != KH_OK) die("[E] %s", kh_last_error(c));
+  FILE *f = fopen(fn.c_str(), "wb");
+  if (!f) return;
+  uint64_t size = n * 20;
+  printf("[D] size data %" PRIu64 "\n[+] Writing file %s ", size, fn.c_str());
+  uint8_t sum[32], hdr[112];
+  sha256_host(bf.data(), bf.size(), sum);
+  fwrite(sum, 1, 32, f);
+  blm_header(hdr, d);
+  fwrite(hdr, 1, 112, f);
+  fwrite(bf.data(), 1, bf.size(), f);
+  sha256_host(table.data(), size, sum);
+  fwrite(sum, 1, 32, f);
+  fwrite(&size, 1, 8, f);
+  fwrite(table.data(), 1, size, f);
+  fclose(f);
+  printf("........\n");
+}
+
 // ---------------------------------------------------------------------------------------------------
 static void menu() {
   printf("\nUsage: keyhunt-b200 -m address|rmd160|xpoint|bsgs -f file [-r A:B | -b bits] [-l compress|uncompress|both] [-c btc|eth]\n"
@@ -496,15 +569,23 @@ int main(int argc, char **argv) {
     printf("[+] N = 0x%" PRIx64 "\n", N_SEQUENTIAL_MAX);
     if (FLAGBITRANGE) printf("[+] Bit Range %i\n", bitrange); else printf("[+] Range \n");
     printf("[+] -- from : 0x%s\n[+] -- to   : 0x%s\n", u_hex(n_range_start).c_str(), u_hex(n_range_end).c_str());
-    std::vector<uint8_t> recs = load_targets(fileName);
+    std::vector<uint8_t> recs, cached_bf;
+    kh_bloom_desc d;
+    bool from_cache = false;
+    std::string cache = FLAGSAVEREADFILE ? dat_name(fileName) : std::string();
+    if (FLAGSAVEREADFILE && dat_read(cache, d, cached_bf, recs)) from_cache = true;   // the reference's -S cache (bloom image reused bit for bit)
+    else recs = load_targets(fileName);
     const uint64_t N = recs.size() / 20;
     printf("[+] Allocating memory for %" PRIu64 " elements: %.2f MB\n", N, (double)(20.0 * N / 1048576.0));
-    kh_bloom_desc d;
-    uint64_t items = (N <= 10000) ? 10000 : (uint64_t)FLAGBLOOMMULTIPLIER * N;   // initBloomFilter keyhunt.cpp:7608
-    kh_bloom_params(items, &d);
-    printf("[+] Bloom filter for %" PRIu64 " elements.\n[+] Loading data to the bloomfilter total: %.2f MB\n", N, (double)d.bytes / 1048576.0);
+    if (!from_cache) {
+      uint64_t items = (N <= 10000) ? 10000 : (uint64_t)FLAGBLOOMMULTIPLIER * N;   // initBloomFilter keyhunt.cpp:7608
+      kh_bloom_params(items, &d);
+      printf("[+] Bloom filter for %" PRIu64 " elements.\n", N);
+    }
+    printf("[+] Loading data to the bloomfilter total: %.2f MB\n", (double)d.bytes / 1048576.0);
     for (kh_ctx *g : gpus)
-      if (kh_set_targets(g, FLAGMODE, FLAGCRYPTO, FLAGSEARCH, recs.data(), N, &d, NULL) != KH_OK) die("[E] %s", kh_last_error(g));
+      if (kh_set_targets(g, FLAGMODE, FLAGCRYPTO, FLAGSEARCH, recs.data(), N, &d, from_cache ? cached_bf.data() : NULL) != KH_OK) die("[E] %s", kh_last_error(g));
+    if (FLAGSAVEREADFILE && !from_cache) dat_write(cache, gpus[0]);
     printf("[+] Sorting data ... done! %" PRIu64 " values were loaded and sorted\n", N);
     fflush(stdout);
     std::vector<std::thread> th;

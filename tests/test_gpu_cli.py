@@ -120,3 +120,32 @@ def test_cli_bsgs_files_and_keys_identical_to_reference(dirs):
     os.remove(os.path.join(g, "KEYFOUNDKEYFOUND.txt"))
     rc, out = run(CLI, args + ["-t", "1"], g)
     assert "tables loaded from files" in out and "All points were found" in out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/keyhunt not built")
+def test_cli_target_cache_file_identical_and_interchangeable(dirs):
+    """-S in scan modes: data_<sha256 prefix>.dat (bloom + sorted table, keyhunt.cpp:7756) is byte-identical to the
+    reference's, and each tool loads the other's file and reports the same keys"""
+    g, r = dirs
+    args = ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:FFFFF", "-l", "compress", "-n", "0x100000", "-S", "-q"]
+    rc_g, out_g = run(CLI, args + ["-t", "1"], g)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "4"], r)
+    assert rc_g == 0 and rc_r == 0, (out_g[-1000:], out_r[-1000:])
+    fg = [f for f in os.listdir(g) if f.startswith("data_")]
+    fr = [f for f in os.listdir(r) if f.startswith("data_")]
+    assert fg == fr and len(fg) == 1
+    a, b = bytearray(open(os.path.join(g, fg[0]), "rb").read()), bytearray(open(os.path.join(r, fr[0]), "rb").read())
+    assert len(a) == len(b)
+    a[32 + 64:32 + 72] = b[32 + 64:32 + 72] = b"\0" * 8      # struct bloom.bf: heap pointer of the writer
+    assert a == b
+    want = records(r, 4)
+    assert records(g, 4) == want and len(want) >= 10
+    # cross-load: swap the cache files, run again with -S: both must say they read the file and find the same keys
+    shutil.copy(os.path.join(r, fr[0]), os.path.join(g, fg[0]))
+    open(os.path.join(r, fr[0]), "wb").write(open(os.path.join(g, fg[0]), "rb").read() if False else bytes(a[:32 + 64]) + bytes(8) + bytes(a[32 + 72:]))
+    for d in (g, r):
+        os.remove(os.path.join(d, "KEYFOUNDKEYFOUND.txt"))
+    rc_g, out_g = run(CLI, args + ["-t", "1"], g)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "4"], r)
+    assert "Reading file data_" in out_g and "Reading file data_" in out_r
+    assert records(g, 4) == want and records(r, 4) == want
