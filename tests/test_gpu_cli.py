@@ -43,7 +43,7 @@ def dirs():
 
 CASES = [
     ("address_compress", ["-m", "address", "-f", GOLD + "/1to32.txt", "-r", "1:FFFFFF", "-l", "compress", "-n", "0x100000"], 4),
-    ("rmd160_both", ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:3FFFFF", "-l", "both", "-n", "0x100000"], 4),
+    ("rmd160_both", ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:FFFFFF", "-l", "both", "-n", "0x100000"], 4),   # ranges end where a racy extra chunk of the reference (cursor checked outside its mutex) cannot contain a target
     ("address_eth", ["-m", "address", "-c", "eth", "-f", GOLD + "/1to32.eth", "-r", "1:FFFFFF", "-n", "0x100000"], 2),
     ("xpoint", ["-m", "xpoint", "-f", GOLD + "/substracted40.txt", "-r", "8000000000:8003000000", "-n", "0x100000"], 4),
     ("stride", ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:FFFFF", "-l", "compress", "-n", "0x100000", "-I", "3"], 4),
@@ -129,7 +129,7 @@ def test_cli_target_cache_file_identical_and_interchangeable(dirs):
     g, r = dirs
     args = ["-m", "rmd160", "-f", GOLD + "/1to32.rmd", "-r", "1:FFFFF", "-l", "compress", "-n", "0x100000", "-S", "-q"]
     rc_g, out_g = run(CLI, args + ["-t", "1"], g)
-    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "4"], r)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "1"], r)   # -t 1: the reference checks the cursor outside its mutex, extra threads overshoot
     assert rc_g == 0 and rc_r == 0, (out_g[-1000:], out_r[-1000:])
     fg = [f for f in os.listdir(g) if f.startswith("data_")]
     fr = [f for f in os.listdir(r) if f.startswith("data_")]
@@ -142,10 +142,10 @@ def test_cli_target_cache_file_identical_and_interchangeable(dirs):
     assert records(g, 4) == want and len(want) >= 10
     # cross-load: swap the cache files, run again with -S: both must say they read the file and find the same keys
     shutil.copy(os.path.join(r, fr[0]), os.path.join(g, fg[0]))
-    open(os.path.join(r, fr[0]), "wb").write(open(os.path.join(g, fg[0]), "rb").read() if False else bytes(a[:32 + 64]) + bytes(8) + bytes(a[32 + 72:]))
+    open(os.path.join(r, fr[0]), "wb").write(bytes(a))       # ours (pointer field zero) into the reference directory
     for d in (g, r):
         os.remove(os.path.join(d, "KEYFOUNDKEYFOUND.txt"))
     rc_g, out_g = run(CLI, args + ["-t", "1"], g)
-    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "4"], r)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "1"], r)   # -t 1: the reference checks the cursor outside its mutex, extra threads overshoot
     assert "Reading file data_" in out_g and "Reading file data_" in out_r
     assert records(g, 4) == want and records(r, 4) == want
