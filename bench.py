@@ -392,7 +392,7 @@ def main():
 
     # ---- CPU baseline: the unmodified reference on a bounded sample of the same workload --------------
     cpu = None
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only
         try:
             cores = os.cpu_count() or 1
             chunks = 16 if w["ops"] > 3000 else 48

@@ -165,3 +165,40 @@ def test_bad_arguments(kh):
         kh.bsgs_build(1 << 21, 1)      # not an even power of two
     with pytest.raises(K.KhError):
         kh.set_targets(K.MODE_BSGS, bytes(20))
+
+
+def test_c3_full_size_planted_only(kh):
+    """BASELINE config 3 at full size: 2^36 keys against 10^6 x-coordinates (999,968 random + 32 planted, bloom 3.6 MB,
+    table 20 MB).  Size-independent property: exactly the planted keys are reported, nothing else."""
+    rnd = random.Random(3)
+    start, n = 0x4000000000000000, 1 << 36
+    idx = sorted({0, n - 1} | {rnd.randrange(n) for _ in range(30)})
+    infos = kh.derive([start + i for i in idx])
+    planted = [be32(info.pub_x)[:20] for info in infos]
+    recs = planted + [rnd.randbytes(20) for _ in range(1000000 - len(planted))]
+    rnd.shuffle(recs)
+    kh.set_targets(K.MODE_XPOINT, b"".join(recs))
+    d, _ = kh.get_bloom()
+    assert (d.entries, d.bits, d.bytes, d.hashes) == (1000000, 28755175, 3594397, 20)     # SURVEY App. A.4
+    got = []
+    for s in range(16):
+        kh.scan(start + s * (n // 16), n // 16)
+        got += [h.key for h in kh.poll_hits()]
+    assert sorted(got) == [start + i for i in idx]
+
+
+def test_c2_quarter_size_planted_only(kh):
+    """BASELINE config 2 (rmd160 -l both, 1,024 targets) on 2^34 keys: compressed and uncompressed planted keys incl. the
+    first and last key of the range and both Y parities; exactly those are reported."""
+    rnd = random.Random(2)
+    start, n = 0x2000000000000000, 1 << 34
+    idx = sorted({0, n - 1} | {rnd.randrange(n) for _ in range(22)})
+    infos = kh.derive([start + i for i in idx])
+    planted = [(info.h160_uncomp if j % 2 else info.h160_comp) for j, info in enumerate(infos)]
+    assert {info.pub_y & 1 for info in infos} == {0, 1}
+    recs = planted + [rnd.randbytes(20) for _ in range(1000)]
+    kh.set_targets(K.MODE_RMD160, b"".join(recs), search=K.SEARCH_BOTH)
+    kh.scan(start, n)
+    hits = kh.poll_hits()
+    assert sorted(h.key for h in hits) == [start + i for i in idx]
+    assert {h.kind for h in hits} == {K.HIT_COMP02, K.HIT_COMP03, K.HIT_UNCOMP}
