@@ -40,9 +40,27 @@ KH_HD uint64_t bloom_mod(uint64_t x, uint64_t bits, uint64_t magic) {
   if (r >= bits) r -= bits;
   return r;
 }
+// single-byte bloom probe.  KH_PROBE_LD selects the load flavour (A/B on the HBM-resident BSGS bloom):
+//   0 = ld.global.nc (LDG.CONSTANT, L1-allocating)   1 = plain ld.global   2 = ld.global.cg (L2 only, no L1)
+//   3 = ld.global.nc.L1::no_allocate
+#ifndef KH_PROBE_LD
+#define KH_PROBE_LD 0
+#endif
 KH_HD uint8_t kh_ld_u8(const uint8_t *p) {
 #ifdef __CUDA_ARCH__
+#if KH_PROBE_LD == 0
   return __ldg(p);
+#elif KH_PROBE_LD == 1
+  return *p;
+#elif KH_PROBE_LD == 2
+  uint32_t v;
+  asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (uint8_t)v;
+#else
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (uint8_t)v;
+#endif
 #else
   return *p;
 #endif
