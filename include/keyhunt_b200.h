@@ -39,7 +39,8 @@ enum { KH_HIT_COMP02 = 0, KH_HIT_COMP03 = 1, KH_HIT_UNCOMP = 2, KH_HIT_ETH = 3, 
 int kh_create(kh_ctx **out, int device_ordinal);
 void kh_destroy(kh_ctx *ctx);
 const char *kh_last_error(kh_ctx *ctx);
-/* tunables: "threads_per_sm" (walker threads per SM), "steps_per_launch", "hit_capacity" */
+/* options: "threads_per_sm" (walker threads per SM), "steps_per_launch", "hit_capacity",
+ * "endomorphism" (1 = the reference's -e: also test beta*x and beta^2*x of every point, keyhunt.cpp:3408-3473) */
 int kh_set_option(kh_ctx *ctx, const char *name, int64_t value);
 
 /* bloom_init2 sizing (bloom/bloom.cpp:154-187) with error = 0.000001 (keyhunt.cpp:7620) */
@@ -75,7 +76,7 @@ typedef struct {
   uint8_t pub_y[32];
   uint8_t matched[20];   /* the 20 bytes found in the table */
   uint8_t kind;          /* KH_HIT_* */
-  uint8_t pad[3];
+  uint8_t pad[3];        /* pad[0]: with "endomorphism" the reference's candidate index l (0..11 BTC, 0..5 ETH, 0..2 xpoint) */
   uint64_t index;        /* point index inside the scanned range */
 } kh_hit;
 /* drains the hits of the scans since the last poll, ascending (index, kind); *n = number written.

@@ -73,7 +73,7 @@ class Stats(C.Structure):
 
 class Hit:
     """One reported key (the reference's writekey record, keyhunt.cpp:6891)."""
-    __slots__ = ("key", "pub_x", "pub_y", "matched", "kind", "index")
+    __slots__ = ("key", "pub_x", "pub_y", "matched", "kind", "index", "variant")
 
     def __init__(self, h):
         self.key = int.from_bytes(bytes(h.key_be), "big")
@@ -82,6 +82,7 @@ class Hit:
         self.matched = bytes(h.matched)
         self.kind = int(h.kind)
         self.index = int(h.index)
+        self.variant = int(h.pad[0])      # -e: the reference's candidate index l
 
     def __repr__(self):
         return "Hit(key=%x kind=%d index=%d matched=%s)" % (self.key, self.kind, self.index, self.matched.hex())

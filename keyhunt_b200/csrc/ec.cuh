@@ -198,4 +198,31 @@ KH_HD void u256_set_u64(u256 &r, uint64_t b) {
   for (int i = 2; i < 8; i++) r.v[i] = 0;
 }
 
+// r = a*b mod n  (Int::ModMulK1order, IntMod.cpp:1111) — only for the -e hit fix-ups (k*lambda), cold
+KH_HD void u256_mulmod_n(u256 &r, const u256 &a, const u256 &b) {
+  const uint32_t n[8] = KH_N;
+  uint32_t t[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) t[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[i] * b.v[j] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+    t[i + 8] = (uint32_t)c;
+  }
+  u256 acc;
+  for (int i = 0; i < 8; i++) acc.v[i] = 0;
+  for (int bit = 511; bit >= 0; bit--) {
+    const uint32_t top = acc.v[7] >> 31;
+    for (int i = 7; i > 0; i--) acc.v[i] = (acc.v[i] << 1) | (acc.v[i - 1] >> 31);
+    acc.v[0] = (acc.v[0] << 1) | ((t[bit >> 5] >> (bit & 31)) & 1u);
+    uint32_t d[8];
+    const uint32_t borrow = kh_sub8(d, acc.v, n);
+    if (top || !borrow) { for (int i = 0; i < 8; i++) acc.v[i] = d[i]; }
+  }
+  r = acc;
+}
+// lambda, lambda^2 as the reference's -e sets them (keyhunt.cpp:928-929)
+#define KH_LAMBDA  {0x1B23BD72u, 0xDF02967Cu, 0x20816678u, 0x122E22EAu, 0x8812645Au, 0xA5261C02u, 0xC05C30E0u, 0x5363AD4Cu}
+#define KH_LAMBDA2 {0xB51283CEu, 0xE0CFC810u, 0x8EC739C2u, 0xA880B9FCu, 0x77ED9BA4u, 0x5AD9E3FDu, 0x3FA3CF1Fu, 0xAC9C52B3u}
+
 }  // namespace kh

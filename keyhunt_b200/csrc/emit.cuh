@@ -18,7 +18,7 @@ struct RawHit {
   uint32_t idx;
   uint32_t kind;
   uint32_t h[5];   // matched 20 bytes as LE words
-  uint32_t pad;
+  uint32_t variant; // with -e: the reference's candidate index l (0..11 BTC, 0..5 ETH, 0..2 xpoint), else 0
 };
 
 struct HitSink {
@@ -35,11 +35,11 @@ KH_HD uint32_t kh_atomic_inc(uint32_t *p) {
   return (*p)++;
 #endif
 }
-KH_HD void sink_push(const HitSink &s, uint64_t batch, uint32_t idx, uint32_t kind, const uint32_t h[5]) {
+KH_HD void sink_push(const HitSink &s, uint64_t batch, uint32_t idx, uint32_t kind, const uint32_t h[5], uint32_t variant = 0) {
   uint32_t slot = kh_atomic_inc(s.count);
   if (slot < s.cap) {
     RawHit r;
-    r.batch = batch; r.idx = idx; r.kind = kind; r.pad = 0;
+    r.batch = batch; r.idx = idx; r.kind = kind; r.variant = variant;
 #pragma unroll
     for (int i = 0; i < 5; i++) r.h[i] = h[i];
     s.hits[slot] = r;
@@ -56,21 +56,69 @@ struct ScanTargets {
   HitSink sink;
 };
 
-template <int KIND>
+// endomorphism constants exactly as the reference's -e sets them (keyhunt.cpp:930-931), little-endian limbs
+#define KH_BETA  {0x719501EEu, 0xC1396C28u, 0x12F58995u, 0x9CF04975u, 0xAC3434E9u, 0x6E64479Eu, 0x657C0710u, 0x7AE96A2Bu}
+#define KH_BETA2 {0x8E6AFA40u, 0x3EC693D6u, 0xED0A766Au, 0x630FB68Au, 0x53CBCB16u, 0x919BB861u, 0x9A83F8EFu, 0x851695D4u}
+
+template <int KIND, bool ENDO = false>
 struct ScanEmit {
   static constexpr bool NEED_Y = (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH || KIND == KH_SCAN_ETH);  // keyhunt.cpp:3294
 #ifndef KH_OUTLINE_MUL
 #define KH_OUTLINE_MUL 1
 #endif
-  static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT);
-  static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT);
+  static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT || ENDO);
+  static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
   const ScanTargets &tg;
   KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
 
-  KH_HDM void probe(const uint32_t h[5], uint32_t kind, uint64_t batch, uint32_t idx) {
+  KH_HDM void probe(const uint32_t h[5], uint32_t kind, uint64_t batch, uint32_t idx, uint32_t variant = 0) {
     if (bloom_check20(tg.bloom, h)) {                  // keyhunt.cpp:3621
       if (table_contains(tg.table, tg.n, h))           // keyhunt.cpp:3623
-        sink_push(tg.sink, batch, idx, kind, h);
+        sink_push(tg.sink, batch, idx, kind, h, variant);
+    }
+  }
+  // -e (FLAGENDOMORPHISM): the candidates x, beta*x, beta^2*x of one point (keyhunt.cpp:3408-3473) through the same
+  // hash/probe code; `variant` is the reference's candidate index l that selects the fix-up on the host
+  // (:3557-3617 compress, :3643-3686 uncompress, :3704-3749 ETH, :3769-3807 xpoint).
+  KH_HDM void point_endo(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
+    uint32_t h[5];
+    const fe b1 = {KH_BETA}, b2 = {KH_BETA2};
+    fe ny;
+    if (NEED_Y) fe_neg(ny, y);
+#pragma unroll 1
+    for (int v = 0; v < 3; v++) {
+      fe xv = x;
+      if (v == 1) fe_mul_sel<OUTLINE_MUL>(xv, x, b1);
+      if (v == 2) fe_mul_sel<OUTLINE_MUL>(xv, x, b2);
+      if (KIND == KH_SCAN_XPOINT) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) h[i] = bswap32(xv.v[7 - i]);
+        probe(h, KH_KIND_XPOINT, batch, idx, (uint32_t)v);
+      }
+      if (KIND == KH_SCAN_ETH) {
+        // slot 2v: (xv, y) — except slot 4, where the reference hashes the BETA point again (keyhunt.cpp:3534);
+        // slot 2v+1: (xv, -y)
+        fe xe = xv;
+        if (v == 2) fe_mul_sel<OUTLINE_MUL>(xe, x, b1);
+        eth_address(h, xe, y);
+        probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v));
+        eth_address(h, xv, ny);
+        probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v + 1));
+      }
+      if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_BOTH) {
+#pragma unroll 1
+        for (int job = 0; job < 2; job++) {
+          hash160_job<NEED_Y>(h, job, xv, y);
+          probe(h, (uint32_t)job, batch, idx, (uint32_t)(2 * v + job));
+        }
+      }
+      if (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {
+#pragma unroll 1
+        for (int neg = 0; neg < 2; neg++) {
+          hash160_job<NEED_Y>(h, 2, xv, neg ? ny : y);
+          probe(h, KH_KIND_UNCOMP, batch, idx, (uint32_t)(6 + 2 * v + neg));
+        }
+      }
     }
   }
   // xpoint: both points of a +-e pair, bloom probes of the two overlapped (keyhunt.cpp:3810-3821 twice)
@@ -86,6 +134,7 @@ struct ScanEmit {
     if (okB && table_contains(tg.table, tg.n, hb)) sink_push(tg.sink, batch, ib, KH_KIND_XPOINT, hb);
   }
   KH_HDM void point(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
+    if (ENDO) { point_endo(x, y, batch, idx); return; }
     uint32_t h[5];
     if (KIND == KH_SCAN_XPOINT) {                      // keyhunt.cpp:3810-3821 (first 20 bytes of X)
 #pragma unroll

@@ -25,6 +25,7 @@ struct kh_ctx {
   int threads_per_sm = 512;
   int steps_per_launch = 16;
   uint32_t hit_capacity = 1u << 16;
+  int endomorphism = 0;            // -e: test beta*x and beta^2*x of every point too
 
   // walk state
   uint64_t T_alloc = 0;            // walker threads the buffers are sized for

@@ -46,13 +46,13 @@ __device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *g
   __syncthreads();
 }
 
-template <int KIND>
+template <int KIND, bool ENDO>
 __global__ void __launch_bounds__(KH_BLOCK, KH_SCAN_MINBLOCKS) kh_scan_kernel(WalkParams wp, ScanTargets tg) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wp.T) return;
-  ScanEmit<KIND> emit(tg);
+  ScanEmit<KIND, ENDO> emit(tg);
   walk_batches(wp, kh_smem_tab, t, emit);
 }
 
@@ -229,6 +229,8 @@ int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
   } else if (!strcmp(name, "steps_per_launch")) {
     if (value < 1 || value > (1 << 20)) return kh_fail(c, KH_EINVAL, "steps_per_launch out of range");
     c->steps_per_launch = (int)value;
+  } else if (!strcmp(name, "endomorphism")) {      // -e (FLAGENDOMORPHISM, keyhunt.cpp:924)
+    c->endomorphism = value ? 1 : 0;
   } else if (!strcmp(name, "hit_capacity")) {
     if (value < 16 || value > (1 << 26)) return kh_fail(c, KH_EINVAL, "hit_capacity out of range");
     c->hit_capacity = (uint32_t)value;
@@ -358,7 +360,8 @@ int kh_get_table(kh_ctx *c, uint8_t *dst20, uint64_t cap_records, uint64_t *n_re
 template <int KIND>
 static cudaError_t launch_scan(kh_ctx *c, const WalkParams &wp, const ScanTargets &tg) {
   const unsigned blocks = (unsigned)(wp.T / KH_BLOCK);
-  kh_scan_kernel<KIND><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
+  if (c->endomorphism) kh_scan_kernel<KIND, true><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
+  else kh_scan_kernel<KIND, false><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
   return cudaGetLastError();
 }
 
@@ -434,7 +437,8 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
     KH_CUDA(c, cudaStreamSynchronize(c->stream));
     std::sort(raw.begin(), raw.end(), [](const RawHit &a, const RawHit &b) {
       const uint64_t ia = a.batch * KH_GRP + a.idx, ib = b.batch * KH_GRP + b.idx;
-      return ia != ib ? ia < ib : a.kind < b.kind;
+      if (ia != ib) return ia < ib;
+      return a.kind != b.kind ? a.kind < b.kind : a.variant < b.variant;
     });
     // keyfound = index*stride + start (keyhunt.cpp:3625-3627)
     std::vector<u256> keys(count);
@@ -442,23 +446,47 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
     std::vector<DevKeyInfo> info;
     rc = derive_dev(c, keys, info);
     if (rc) return rc;
-    // compressed matches are parity-blind: if the real prefix differs from the matched one the
-    // target's key is n - k (keyhunt.cpp:3629-3634)
-    std::vector<uint32_t> flip;
-    for (uint32_t i = 0; i < count; i++) {
-      const uint32_t odd = info[i].y[0] & 1u;
-      if ((raw[i].kind == KH_KIND_COMP02 && odd) || (raw[i].kind == KH_KIND_COMP03 && !odd)) flip.push_back(i);
+    auto negate = [&](uint32_t i) { u256 nk; u256_neg_mod_n(nk, keys[i]); keys[i] = nk; };
+    if (!c->endomorphism) {
+      // compressed matches are parity-blind: if the real prefix differs from the matched one the
+      // target's key is n - k (keyhunt.cpp:3629-3634)
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t odd = info[i].y[0] & 1u;
+        if ((raw[i].kind == KH_KIND_COMP02 && odd) || (raw[i].kind == KH_KIND_COMP03 && !odd)) negate(i);
+      }
+    } else {
+      // -e fix-ups, candidate index l = raw.variant: multiply by lambda^(l/2) (ModMulK1order), then
+      //   compress  (keyhunt.cpp:3566-3613): negate by the parity of the ORIGINAL key's Y against the matched prefix
+      //   uncompress (:3652-3682) / ETH (:3714-3744): recompute the hash of the candidate key, negate on mismatch
+      //   xpoint    (:3782-3806): no negation
+      const u256 lam[3] = {{{1, 0, 0, 0, 0, 0, 0, 0}}, {KH_LAMBDA}, {KH_LAMBDA2}};
+      std::vector<uint32_t> recheck;
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t l = raw[i].variant, kind = raw[i].kind;
+        const uint32_t v = (kind == KH_KIND_UNCOMP) ? (l - 6) / 2 : (kind == KH_KIND_XPOINT ? l : l / 2);
+        const uint32_t odd = info[i].y[0] & 1u;
+        if (v) { u256 t; u256_mulmod_n(t, keys[i], lam[v]); keys[i] = t; }
+        if (kind == KH_KIND_COMP02 || kind == KH_KIND_COMP03) {
+          if ((kind == KH_KIND_COMP02 && odd) || (kind == KH_KIND_COMP03 && !odd)) negate(i);
+        } else if (kind == KH_KIND_UNCOMP || kind == KH_KIND_ETH) {
+          recheck.push_back(i);
+        }
+      }
+      if (!recheck.empty()) {
+        std::vector<u256> k2(recheck.size());
+        for (size_t j = 0; j < recheck.size(); j++) k2[j] = keys[recheck[j]];
+        std::vector<DevKeyInfo> i2;
+        rc = derive_dev(c, k2, i2);
+        if (rc) return rc;
+        for (size_t j = 0; j < recheck.size(); j++) {
+          const uint32_t i = recheck[j];
+          const uint32_t *hh = (raw[i].kind == KH_KIND_ETH) ? i2[j].eth : i2[j].hu;
+          if (memcmp(hh, raw[i].h, 20) != 0) negate(i);
+        }
+      }
     }
-    for (uint32_t i : flip) {
-      u256 nk;
-      u256_neg_mod_n(nk, keys[i]);
-      keys[i] = nk;
-      // -P has the same X and the negated Y
-      fe y, ny;
-      for (int k = 0; k < 8; k++) y.v[k] = info[i].y[k];
-      fe_neg(ny, y);
-      for (int k = 0; k < 8; k++) info[i].y[k] = ny.v[k];
-    }
+    rc = derive_dev(c, keys, info);       // public keys of the keys that are reported
+    if (rc) return rc;
     for (uint32_t i = 0; i < count; i++) {
       kh_hit h;
       memset(&h, 0, sizeof(h));
@@ -467,6 +495,7 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
       limbs_to_be(h.pub_y, info[i].y);
       words_to_bytes20(h.matched, raw[i].h);
       h.kind = (uint8_t)raw[i].kind;
+      h.pad[0] = (uint8_t)raw[i].variant;
       h.index = raw[i].batch * KH_GRP + raw[i].idx;
       c->ready_hits.push_back(h);
     }

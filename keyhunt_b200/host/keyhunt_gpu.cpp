@@ -8,8 +8,8 @@
 // file checksums, and one modular square root per BSGS public key to decompress it).
 //
 //   -t N   number of GPUs to use (the reference's worker-thread count); default 1
-// Modes outside the GPU path (vanity, minikeys, pub2rmd), -R random, -e endomorphism and the mmap'd
-// bloom/ptable flags are parsed; the former are refused, the latter accepted and ignored (tables live in HBM).
+// Modes outside the GPU path (vanity, minikeys, pub2rmd), -R random and the mmap'd bloom/ptable flags are
+// parsed; the former are refused, the latter accepted and ignored (tables live in HBM).  -e is supported.
 #include <getopt.h>
 #include <inttypes.h>
 #include <math.h>
@@ -198,7 +198,7 @@ static bool decompress_pub(const uint8_t x_be[32], int odd, uint8_t y_be[32]) {
 // ---------------------------------------------------------------------------------------------------
 static int FLAGMODE = KH_MODE_ADDRESS, FLAGCRYPTO = 0, FLAGSEARCH = KH_SEARCH_BOTH, NGPUS = 1, KFACTOR = 1;
 static int FLAGQUIET = 0, FLAGMATRIX = 0, FLAGSAVEREADFILE = 0, FLAGSKIPCHECKSUM = 0, FLAGBITRANGE = 0, FLAGRANGE = 0, FLAG_N = 0;
-static int FLAGBLOOMMULTIPLIER = 1, OUTPUTSECONDS = 30;
+static int FLAGBLOOMMULTIPLIER = 1, OUTPUTSECONDS = 30, FLAGENDOMORPHISM = 0;
 static const char *fileName = "addresses.txt", *str_N = nullptr;
 static U256 n_range_start, n_range_end, stride_v;
 static uint64_t N_SEQUENTIAL_MAX = 0x100000000ULL;
@@ -485,7 +485,7 @@ int main(int argc, char **argv) {
       case 'q': FLAGQUIET = 1; printf("[+] Quiet thread output\n"); break;
       case 'S': FLAGSAVEREADFILE = 1; break;
       case 'R': die("[E] -R (random mode) uses the OS RNG and is not reproducible; not supported by the GPU back end");
-      case 'e': die("[E] -e (endomorphism) is not supported by the GPU back end yet");
+      case 'e': FLAGENDOMORPHISM = 1; printf("[+] Endomorphism enabled\n"); break;
       case 'B': if (strcmp(optarg, "sequential")) die("[E] only -B sequential is supported (got %s)", optarg); break;
       case 'b': bitrange = atoi(optarg); if (bitrange > 0 && bitrange <= 256) FLAGBITRANGE = 1; else fprintf(stderr, "[E] invalid bits param: %s.\n", optarg); break;
       case 'c': if (!strcmp(optarg, "btc")) FLAGCRYPTO = KH_CRYPTO_BTC; else if (!strcmp(optarg, "eth")) { FLAGCRYPTO = KH_CRYPTO_ETH; printf("[+] Setting search for ETH adddress.\n"); } else die("[E] Unknow crypto value %s", optarg); break;
@@ -525,6 +525,7 @@ int main(int argc, char **argv) {
   }
   if (FLAGMODE == KH_MODE_ADDRESS && FLAGCRYPTO == 0) { FLAGCRYPTO = KH_CRYPTO_BTC; printf("[+] Setting search for btc adddress\n"); }
   if (FLAGMODE == KH_MODE_BSGS) printf("[+] Mode BSGS sequential\n");
+  if (FLAGMODE == KH_MODE_BSGS && FLAGENDOMORPHISM) die("[E] Endomorphism doesn't work with BSGS");
 
   // range (keyhunt.cpp:1221-1262, :854-873)
   U256 order; memcpy(order.b, ORDER_N, 32);
@@ -583,8 +584,10 @@ int main(int argc, char **argv) {
       printf("[+] Bloom filter for %" PRIu64 " elements.\n", N);
     }
     printf("[+] Loading data to the bloomfilter total: %.2f MB\n", (double)d.bytes / 1048576.0);
-    for (kh_ctx *g : gpus)
+    for (kh_ctx *g : gpus) {
+      if (kh_set_option(g, "endomorphism", FLAGENDOMORPHISM) != KH_OK) die("[E] %s", kh_last_error(g));
       if (kh_set_targets(g, FLAGMODE, FLAGCRYPTO, FLAGSEARCH, recs.data(), N, &d, from_cache ? cached_bf.data() : NULL) != KH_OK) die("[E] %s", kh_last_error(g));
+    }
     if (FLAGSAVEREADFILE && !from_cache) dat_write(cache, gpus[0]);
     printf("[+] Sorting data ... done! %" PRIu64 " values were loaded and sorted\n", N);
     fflush(stdout);
@@ -593,7 +596,9 @@ int main(int argc, char **argv) {
     for (auto &t : th) t.join();
     clock_gettime(CLOCK_MONOTONIC, &t1);
     double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-    uint64_t shown = total_points.load() * ((FLAGSEARCH == KH_SEARCH_COMPRESS) ? 2 : 1);                 // keyhunt.cpp:2889-2891
+    uint64_t shown = total_points.load();                                                                // keyhunt.cpp:2883-2891
+    if (FLAGENDOMORPHISM) shown *= (FLAGMODE == KH_MODE_XPOINT) ? 3 : 6;
+    else if (FLAGSEARCH == KH_SEARCH_COMPRESS) shown *= 2;
     printf("\r[+] Total %" PRIu64 " keys in %.0f seconds: ~%.0f Mkeys/s (%.0f keys/s)\n", shown, secs, shown / secs / 1e6, shown / secs);
     printf("\nEnd\n");
   } else {

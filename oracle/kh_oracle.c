@@ -29,6 +29,11 @@ static const fe FE_N = {{0xBFD25E8CD0364141ULL, 0xBAAEDCE6AF48A03BULL, 0xFFFFFFF
 static const ge GE_G = {{{0x59F2815B16F81798ULL, 0x029BFCDB2DCE28D9ULL, 0x55A06295CE870B07ULL, 0x79BE667EF9DCBBACULL}},
                         {{0x9C47D08FFB10D4B8ULL, 0xFD17B448A6855419ULL, 0x5DA4FBFC0E1108A8ULL, 0x483ADA7726A3C465ULL}}};
 #define K1C 0x1000003D1ULL /* 2^256 mod P */
+/* endomorphism constants exactly as the -e option sets them (keyhunt.cpp:928-931) */
+static const fe SC_LAMBDA = {{0xDF02967C1B23BD72ULL, 0x122E22EA20816678ULL, 0xA5261C028812645AULL, 0x5363AD4CC05C30E0ULL}};
+static const fe SC_LAMBDA2 = {{0xE0CFC810B51283CEULL, 0xA880B9FC8EC739C2ULL, 0x5AD9E3FD77ED9BA4ULL, 0xAC9C52B33FA3CF1FULL}};
+static const fe FE_BETA = {{0xC1396C28719501EEULL, 0x9CF0497512F58995ULL, 0x6E64479EAC3434E9ULL, 0x7AE96A2B657C0710ULL}};
+static const fe FE_BETA2 = {{0x3EC693D68E6AFA40ULL, 0x630FB68AED0A766AULL, 0x919BB86153CBCB16ULL, 0x851695D49A83F8EFULL}};
 
 /* ------------------------------------------------------------------------------------------------
  * 256-bit helpers (Int.cpp)
@@ -71,6 +76,24 @@ static void u256_set_u64(fe *r, uint64_t v) { r->l[0] = v; r->l[1] = r->l[2] = r
 static void u256_mul_u64(fe *r, const fe *a, uint64_t b) {
   u128 c = 0;
   for (int i = 0; i < 4; i++) { c += (u128)a->l[i] * b; r->l[i] = (uint64_t)c; c >>= 64; }
+}
+
+/* r = a*b mod n  (Int::ModMulK1order IntMod.cpp:1111; value only, restated as product + binary reduction) */
+static void sc_mul(fe *r, const fe *a, const fe *b) {
+  uint64_t t[8] = {0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a->l[i] * b->l[j] + t[i + j]; t[i + j] = (uint64_t)c; c >>= 64; }
+    t[i + 4] = (uint64_t)c;
+  }
+  fe acc; u256_set_u64(&acc, 0);
+  for (int bit = 511; bit >= 0; bit--) {
+    uint64_t top = acc.l[3] >> 63;
+    for (int i = 3; i > 0; i--) acc.l[i] = (acc.l[i] << 1) | (acc.l[i - 1] >> 63);
+    acc.l[0] = (acc.l[0] << 1) | ((t[bit / 64] >> (bit % 64)) & 1);
+    if (top || u256_cmp(&acc, &FE_N) >= 0) u256_sub(&acc, &acc, &FE_N);
+  }
+  *r = acc;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -596,13 +619,15 @@ int kho_searchbinary(void *h, const uint8_t data[20]) { /* keyhunt.cpp:3065-3089
  * Scan (thread_process keyhunt.cpp:3265-3861)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  otargets *t; int mode, crypto, search;
+  otargets *t; int mode, crypto, search, endo;
   fe start, stride; const gtable *tab;
   uint64_t batch0, batch1;
   kho_hit *hits; uint64_t nhits, cap;
 } scan_job;
 
-static void job_push(scan_job *j, const fe *key, const uint8_t m[20], int kind, uint64_t index) {
+static void job_push_v(scan_job *j, const fe *key, const uint8_t m[20], int kind, uint64_t index, int variant);
+static void job_push(scan_job *j, const fe *key, const uint8_t m[20], int kind, uint64_t index) { job_push_v(j, key, m, kind, index, 0); }
+static void job_push_v(scan_job *j, const fe *key, const uint8_t m[20], int kind, uint64_t index, int variant) {
   if (j->nhits == j->cap) {
     j->cap = j->cap ? j->cap * 2 : 16;
     j->hits = (kho_hit *)realloc(j->hits, j->cap * sizeof(kho_hit));
@@ -612,11 +637,78 @@ static void job_push(scan_job *j, const fe *key, const uint8_t m[20], int kind, 
   fe_to_be(h->key_be, key);
   memcpy(h->matched, m, 20);
   h->kind = (uint8_t)kind;
+  h->pad[0] = (uint8_t)variant;
   h->index = index;
 }
 static int probe(otargets *t, const uint8_t h[20]) { /* bloom_check then searchbinary, keyhunt.cpp:3621-3624 */
   return kho_bloom_check(t->bloom, h, 20) && kho_searchbinary(t, h);
 }
+
+/* -e: the six (three for xpoint) endomorphic candidates of one point and their hit fix-ups, exactly as
+ * thread_process does them (keyhunt.cpp:3408-3473 candidates, :3483-3516/:3525-3536 hashes, :3557-3617,
+ * :3643-3686, :3704-3749, :3769-3807 fix-ups) — including the ETH slot 4 that hashes the beta point again
+ * (:3534) and therefore reports a key that does not own the address. variant = the reference's index l. */
+static void scan_point_endo(scan_job *j, const ge *p, const fe *key, uint64_t index) {
+  uint8_t h[20], h2[20];
+  ge q[3];
+  q[0] = *p;
+  q[1].y = p->y; fe_mul(&q[1].x, &p->x, &FE_BETA);
+  q[2].y = p->y; fe_mul(&q[2].x, &p->x, &FE_BETA2);
+  const fe *lam[3] = {NULL, &SC_LAMBDA, &SC_LAMBDA2};
+  if (j->mode == KHO_MODE_XPOINT) {
+    for (int v = 0; v < 3; v++) {
+      uint8_t x[32];
+      fe_to_be(x, &q[v].x);
+      if (probe(j->t, x)) { fe kk = *key; if (v) sc_mul(&kk, &kk, lam[v]); job_push_v(j, &kk, x, KHO_HIT_XPOINT, index, v); }
+    }
+    return;
+  }
+  if (j->crypto == KHO_CRYPTO_ETH) {
+    for (int l = 0; l < 6; l++) {
+      ge c = q[l / 2];
+      if (l == 4) c = q[1];                                   /* :3534 hashes endomorphism_beta again */
+      if (l & 1) { if (l == 5) c = q[2]; fe_neg(&c.y, &c.y); }
+      eth_addr_ge(&c, h);
+      if (!probe(j->t, h)) continue;
+      fe kk = *key; ge pub;
+      if (l >= 2) sc_mul(&kk, &kk, lam[l / 2]);
+      ge_scalar_mul(&pub, &GE_G, &kk);
+      eth_addr_ge(&pub, h2);
+      if (memcmp(h, h2, 20) != 0) u256_sub(&kk, &FE_N, &kk);
+      job_push_v(j, &kk, h, KHO_HIT_ETH, index, l);
+    }
+    return;
+  }
+  ge pub0;                                                    /* publickey = ComputePublicKey(keyfound) before any lambda */
+  int have_pub0 = 0;
+  if (j->search == KHO_SEARCH_COMPRESS || j->search == KHO_SEARCH_BOTH) {
+    for (int l = 0; l < 6; l++) {
+      hash160_comp_fe((l & 1) ? 0x03 : 0x02, &q[l / 2].x, h);
+      if (!probe(j->t, h)) continue;
+      fe kk = *key;
+      if (!have_pub0) { ge_scalar_mul(&pub0, &GE_G, &kk); have_pub0 = 1; }
+      int odd = (int)(pub0.y.l[0] & 1);
+      if (l >= 2) sc_mul(&kk, &kk, lam[l / 2]);
+      if (((l & 1) == 0 && odd) || ((l & 1) == 1 && !odd)) u256_sub(&kk, &FE_N, &kk);
+      job_push_v(j, &kk, h, (l & 1) ? KHO_HIT_COMP03 : KHO_HIT_COMP02, index, l);
+    }
+  }
+  if (j->search == KHO_SEARCH_UNCOMPRESS || j->search == KHO_SEARCH_BOTH) {
+    for (int l = 6; l < 12; l++) {
+      ge c = q[(l - 6) / 2];
+      if (l & 1) fe_neg(&c.y, &c.y);
+      hash160_uncomp_ge(&c, h);
+      if (!probe(j->t, h)) continue;
+      fe kk = *key; ge pub;
+      if (l >= 8) sc_mul(&kk, &kk, lam[(l - 6) / 2]);
+      ge_scalar_mul(&pub, &GE_G, &kk);
+      hash160_uncomp_ge(&pub, h2);
+      if (memcmp(h, h2, 20) != 0) u256_sub(&kk, &FE_N, &kk);
+      job_push_v(j, &kk, h, KHO_HIT_UNCOMP, index, l);
+    }
+  }
+}
+
 static void *scan_worker(void *arg) {
   scan_job *j = (scan_job *)arg;
   ge *pts = (ge *)malloc(sizeof(ge) * GRP);
@@ -644,6 +736,7 @@ static void *scan_worker(void *arg) {
       u256_mul_u64(&ik, &j->stride, (uint64_t)i);
       u256_add(&key, &base, &ik);                                  /* keyfound = k*stride + key_mpz :3625-3627 */
       uint64_t index = b * GRP + (uint64_t)i;
+      if (j->endo) { scan_point_endo(j, &pts[i], &key, index); continue; }
       if (j->mode == KHO_MODE_XPOINT) {                            /* :3810-3821 */
         uint8_t x[32];
         fe_to_be(x, &pts[i].x);
@@ -679,8 +772,8 @@ static void *scan_worker(void *arg) {
   return NULL;
 }
 
-int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t start[32], const uint8_t stride_be[32],
-                 uint64_t n_points, kho_hit *hits, uint64_t max_hits, int nthreads) {
+int64_t kho_scan_ex(void *targets, int mode, int crypto, int search, int endo, const uint8_t start[32], const uint8_t stride_be[32],
+                    uint64_t n_points, kho_hit *hits, uint64_t max_hits, int nthreads) {
   if (n_points % GRP) return -1;
   uint64_t nb = n_points / GRP;
   if (nthreads < 1) nthreads = 1;
@@ -694,7 +787,7 @@ int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t 
   pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
   for (int i = 0; i < nthreads; i++) {
     scan_job *j = &jobs[i];
-    j->t = (otargets *)targets; j->mode = mode; j->crypto = crypto; j->search = search;
+    j->t = (otargets *)targets; j->mode = mode; j->crypto = crypto; j->search = search; j->endo = endo;
     fe_from_be(&j->start, start); j->stride = stride; j->tab = tab;
     j->batch0 = nb * (uint64_t)i / (uint64_t)nthreads;
     j->batch1 = nb * (uint64_t)(i + 1) / (uint64_t)nthreads;
@@ -711,6 +804,11 @@ int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t 
   }
   free(jobs); free(th); free(tab);
   return total;
+}
+
+int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t start[32], const uint8_t stride_be[32],
+                 uint64_t n_points, kho_hit *hits, uint64_t max_hits, int nthreads) {
+  return kho_scan_ex(targets, mode, crypto, search, 0, start, stride_be, n_points, hits, max_hits, nthreads);
 }
 
 /* ------------------------------------------------------------------------------------------------

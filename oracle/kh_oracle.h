@@ -58,7 +58,7 @@ typedef struct {
   uint8_t key_be[32];   /* reported private key (after the n-k fix-up of keyhunt.cpp:3629-3635)    */
   uint8_t matched[20];  /* the 20 bytes that matched the table                                    */
   uint8_t kind;         /* KHO_HIT_*                                                               */
-  uint8_t pad[3];
+  uint8_t pad[3];       /* pad[0] = with -e: the reference's candidate index l (0..11 BTC, 0..5 ETH, 0..2 xpoint) */
   uint64_t index;       /* point index inside the scanned range (key = start + index*stride)      */
 } kho_hit;
 
@@ -75,6 +75,11 @@ int kho_searchbinary(void *t, const uint8_t data[20]);  /* keyhunt.cpp:3065 */
 int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t start[32],
                  const uint8_t stride[32], uint64_t n_points, kho_hit *hits, uint64_t max_hits,
                  int nthreads);
+
+/* the same with FLAGENDOMORPHISM (-e, keyhunt.cpp:3408-3473, :3556-3618): endo != 0 tests the six (xpoint: three)
+ * endomorphic candidates of every point and applies the reference's lambda / negation fix-ups */
+int64_t kho_scan_ex(void *targets, int mode, int crypto, int search, int endo, const uint8_t start[32],
+                    const uint8_t stride[32], uint64_t n_points, kho_hit *hits, uint64_t max_hits, int nthreads);
 
 /* ---- BSGS (keyhunt.cpp:1450-1842 setup, :5284 thread_bPload, :4549 thread_process_bsgs) -------- */
 typedef struct {

@@ -14,6 +14,11 @@ REF_BIN = os.path.join(ORACLE_DIR, "_ref", "keyhunt")
 REF_BIN_V3 = os.path.join(ORACLE_DIR, "_ref", "keyhunt_v3")
 
 N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+# -e constants as the reference sets them (keyhunt.cpp:928-931)
+LAMBDA = 0x5363ad4cc05c30e0a5261c028812645a122e22ea20816678df02967c1b23bd72
+LAMBDA2 = 0xac9c52b33fa3cf1f5ad9e3fd77ed9ba4a880b9fc8ec739c2e0cfc810b51283ce
+BETA = 0x7ae96a2b657c07106e64479eac3434e99cf0497512f58995c1396c28719501ee
+BETA2 = 0x851695d49a83f8ef919bb86153cbcb16630fb68aed0a766a3ec693d68e6afa40
 P_FIELD = 2**256 - 2**32 - 977
 
 MODE_XPOINT, MODE_ADDRESS, MODE_RMD160 = 0, 1, 2
@@ -154,6 +159,8 @@ class Oracle(_Lib):
         self._sig("searchbinary", C.c_int, [C.c_void_p, u8p])
         self._sig("scan", C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_uint64,
                                       C.POINTER(Hit), C.c_uint64, C.c_int])
+        self._sig("scan_ex", C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_uint64,
+                                         C.POINTER(Hit), C.c_uint64, C.c_int])
         self._sig("bsgs_new", C.c_void_p, [C.c_uint64, C.c_uint32, C.c_int])
         self._sig("bsgs_free", None, [C.c_void_p])
         self._sig("bsgs_params", None, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 5)
@@ -184,16 +191,16 @@ class Oracle(_Lib):
     def searchbinary(self, t, rec: bytes):
         return self._searchbinary(t, rec)
 
-    def scan(self, t, mode, crypto, search, start, stride, n_points, nthreads=8, max_hits=4096):
+    def scan(self, t, mode, crypto, search, start, stride, n_points, nthreads=8, max_hits=4096, endo=False):
         hits = (Hit * max_hits)()
-        n = self._scan(t, mode, crypto, search, be32(start), be32(stride), n_points, hits, max_hits, nthreads)
+        n = self._scan_ex(t, mode, crypto, search, 1 if endo else 0, be32(start), be32(stride), n_points, hits, max_hits, nthreads)
         if n < 0:
             raise ValueError("kho_scan: n_points must be a multiple of 1024")
         out = []
         for i in range(min(n, max_hits)):
             h = hits[i]
             out.append(dict(key=int.from_bytes(bytes(h.key_be), "big"), matched=bytes(h.matched),
-                            kind=int(h.kind), index=int(h.index)))
+                            kind=int(h.kind), index=int(h.index), variant=int(h.pad[0])))
         return out
 
     # bsgs

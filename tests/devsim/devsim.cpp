@@ -41,7 +41,7 @@ uint64_t ds_xxh64_32(const uint8_t b[32], uint64_t seed) { uint32_t w[8]; memcpy
 uint64_t ds_bloom_mod(uint64_t x, uint64_t bits) { return bloom_mod(x, bits, (~0ULL) / bits); }
 
 // ---- scan emulation: what the host API + kernels do, with T walker "threads" run one after another ----
-struct DsHit { uint64_t index; uint32_t kind; uint8_t matched[20]; uint32_t pad; };
+struct DsHit { uint64_t index; uint32_t kind; uint8_t matched[20]; uint32_t variant; };
 
 static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vector<uint32_t> &centers, std::vector<kh_u4> &scratch) {
   gtab.resize(KH_TAB_WORDS);
@@ -58,7 +58,7 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
 // kind: KH_SCAN_*; table20: N sorted 20-byte records; bloom image as bytes
 int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint8_t *bloom_bytes, uint64_t bloom_bits,
                 uint32_t bloom_hashes, const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T,
-                uint32_t steps_per_launch, DsHit *out, uint32_t max_hits) {
+                uint32_t steps_per_launch, DsHit *out, uint32_t max_hits, int endo) {
   WalkSetup ws;
   memset(&ws, 0, sizeof(ws));
   u256_from_be(ws.s, stride);
@@ -88,12 +88,17 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;
     for (uint64_t t = 0; t < T; t++) {
-      switch (kind) {
+      switch (kind + (endo ? 8 : 0)) {
         case KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         default: return -1;
       }
     }
@@ -103,7 +108,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
     out[i].index = raw[i].batch * KH_GRP + raw[i].idx;
     out[i].kind = raw[i].kind;
     words_to_bytes(out[i].matched, raw[i].h);
-    out[i].pad = 0;
+    out[i].variant = raw[i].variant;
   }
   return count;
 }

@@ -149,6 +149,55 @@ def scans(o):
     return out
 
 
+def endo_scans(o):
+    """-e runs of the unmodified reference on planted endomorphic targets -> scans_endo.json"""
+    from _oracle import BETA, BETA2
+    P = P_FIELD
+    out = []
+    d = tempfile.mkdtemp(prefix="khgold_")
+    try:
+        rnd = random.Random(77)
+        start, n = 0x3000000000000000, 1 << 21
+        idx = [0, 1, 1023, 1024, n - 1] + [rnd.randrange(n) for _ in range(19)]
+        comp, unc, eth, xp = [], [], [], []
+        for j, i in enumerate(idx):
+            x, y = o.pubkey(start + i)
+            xs = [x, x * BETA % P, x * BETA2 % P]
+            v = j % 3
+            pre = (2 + (y & 1)) if (j // 3) % 2 == 0 else (3 - (y & 1))          # real and opposite parity
+            comp.append(o.hash160_comp(pre, xs[v]).hex())
+            yy = y if (j // 3) % 2 == 0 else P - y
+            unc.append(o.hash160_uncomp(xs[v], yy).hex())
+            eth.append("0x" + o.eth_addr(xs[v], yy).hex())
+            xp.append("%064x" % xs[v])
+        decoys = [rnd.randbytes(20).hex() for _ in range(40)]
+        files = {"comp": comp + decoys, "unc": unc + decoys, "both": comp[:12] + unc[12:] + decoys,
+                 "eth": eth + ["0x" + t for t in decoys], "xp": xp + [rnd.randbytes(32).hex() for _ in range(40)]}
+        for nm, lst in files.items():
+            open(os.path.join(d, nm + ".txt"), "w").write("\n".join(lst) + "\n")
+        rng = "%x:%x" % (start, start + n)
+        cases = [("endo_compress", ["-m", "rmd160", "-f", d + "/comp.txt", "-l", "compress"], "comp"),
+                 ("endo_uncompress", ["-m", "rmd160", "-f", d + "/unc.txt", "-l", "uncompress"], "unc"),
+                 ("endo_both", ["-m", "rmd160", "-f", d + "/both.txt", "-l", "both"], "both"),
+                 ("endo_eth", ["-m", "address", "-c", "eth", "-f", d + "/eth.txt"], "eth"),
+                 ("endo_xpoint", ["-m", "xpoint", "-f", d + "/xp.txt"], "xp")]
+        for name, args, nm in cases:
+            stdout = run_ref(args + ["-e", "-r", rng, "-n", "0x100000", "-q", "-s", "0", "-t", "2"], d)
+            assert "End" in stdout, stdout[-1500:]
+            fn = os.path.join(d, "KEYFOUNDKEYFOUND.txt")
+            lines = open(fn).read().splitlines() if os.path.exists(fn) else []
+            per = 2 if nm == "eth" else 4
+            recs = sorted("|".join(lines[i:i + per]) for i in range(0, len(lines), per))
+            if os.path.exists(fn):
+                os.remove(fn)
+            out.append({"name": name, "args": " ".join(a.replace(d + "/", "") for a in args) + " -e -r " + rng + " -n 0x100000",
+                        "targets": files[nm], "records": recs})
+            print(name, len(recs))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def bsgs():
     d = tempfile.mkdtemp(prefix="khgold_")
     out = {}
@@ -193,4 +242,5 @@ if __name__ == "__main__":
     json.dump(primitives(r), open(os.path.join(HERE, "primitives.json"), "w"), indent=0)
     json.dump(scans(o), open(os.path.join(HERE, "scans.json"), "w"), indent=0)
     json.dump(bsgs(), open(os.path.join(HERE, "bsgs.json"), "w"), indent=0)
+    json.dump(endo_scans(o), open(os.path.join(HERE, "scans_endo.json"), "w"), indent=0)
     print("golden vectors written")

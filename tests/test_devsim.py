@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class DsHit(C.Structure):
-    _fields_ = [("index", C.c_uint64), ("kind", C.c_uint32), ("matched", C.c_uint8 * 20), ("pad", C.c_uint32)]
+    _fields_ = [("index", C.c_uint64), ("kind", C.c_uint32), ("matched", C.c_uint8 * 20), ("variant", C.c_uint32)]
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +28,7 @@ def ds():
     lib.ds_bloom_mod.restype = C.c_uint64; lib.ds_bloom_mod.argtypes = [C.c_uint64, C.c_uint64]
     lib.ds_scan.restype = C.c_int64
     lib.ds_scan.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint32, C.c_char_p, C.c_char_p,
-                            C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(DsHit), C.c_uint32]
+                            C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(DsHit), C.c_uint32, C.c_int]
     lib.ds_walk_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_char_p]
     return lib
 
@@ -122,8 +122,44 @@ def test_scan_emit_logic(ds, oracle, name):
     d = oracle.bloom_desc(bl)
     hits = (DsHit * 256)()
     cnt = ds.ds_scan(kind, oracle.targets_table(t), len(recs), oracle.bloom_bytes(bl), d["bits"], d["hashes"], be32(start),
-                     be32(stride), nb, T, 2, hits, 256)
+                     be32(stride), nb, T, 2, hits, 256, 0)
     oracle.targets_free(t)
     got = sorted((hits[i].index, hits[i].kind, bytes(hits[i].matched)) for i in range(cnt))
     assert got == sorted((h["index"], h["kind"], h["matched"]) for h in want)
+    assert cnt >= 10
+
+
+@pytest.mark.parametrize("name", sorted(KINDS))
+def test_scan_emit_logic_endomorphism(ds, oracle, name):
+    """-e candidates (x, beta*x, beta^2*x; +-y; the ETH slot-4 quirk): raw device hits (index, kind, l, matched) == oracle"""
+    from _oracle import BETA, BETA2
+    kind, mode, crypto, search = KINDS[name]
+    rnd = random.Random(hash(name) & 0xFFF)
+    start, stride, nb, T = 0x3000000000000321, 1, 3, 2
+    n = nb * 1024
+    P = P_FIELD
+    recs = []
+    for j, i in enumerate(sorted({0, 512, 1023, 1024, n - 1} | {rnd.randrange(n) for _ in range(13)})):
+        x, y = oracle.pubkey(start + i * stride)
+        xv = [x, x * BETA % P, x * BETA2 % P][j % 3]
+        yy = y if (j // 3) % 2 == 0 else P - y
+        if name == "xpoint":
+            recs.append(be32(xv)[:20])
+        elif name == "eth":
+            recs.append(oracle.eth_addr(xv, yy))
+        elif name == "comp" or (name == "both" and j % 2):
+            recs.append(oracle.hash160_comp(2 + (yy & 1), xv))
+        else:
+            recs.append(oracle.hash160_uncomp(xv, yy))
+    recs += [rnd.randbytes(20) for _ in range(60)]
+    t = oracle.targets_new(b"".join(recs))
+    want = oracle.scan(t, mode, crypto, search, start, stride, n, nthreads=2, endo=True)
+    bl = oracle.targets_bloom(t)
+    d = oracle.bloom_desc(bl)
+    hits = (DsHit * 256)()
+    cnt = ds.ds_scan(kind, oracle.targets_table(t), len(recs), oracle.bloom_bytes(bl), d["bits"], d["hashes"], be32(start),
+                     be32(stride), nb, T, 2, hits, 256, 1)
+    oracle.targets_free(t)
+    got = sorted((hits[i].index, hits[i].kind, hits[i].variant, bytes(hits[i].matched)) for i in range(cnt))
+    assert got == sorted((h["index"], h["kind"], h["variant"], h["matched"]) for h in want)
     assert cnt >= 10
