@@ -57,7 +57,7 @@ def test_endomorphism_hits_equal_oracle(kh, oracle, name, mode, crypto, search, 
     t = oracle.targets_new(b"".join(recs))
     want = oracle.scan(t, omode, ocrypto, osearch, start, stride, n, endo=True)
     oracle.targets_free(t)
-    assert sorted((h.index, h.kind, h.variant, h.key, h.matched) for h in got) == \\
+    assert sorted((h.index, h.kind, h.variant, h.key, h.matched) for h in got) == \
            sorted((h["index"], h["kind"], h["variant"], h["key"], h["matched"]) for h in want)
     assert len(got) >= 20
     for h in got:
@@ -71,7 +71,7 @@ def test_cli_endomorphism_records_equal_reference(name):
     d = tempfile.mkdtemp(prefix="khendo_")
     try:
         fn = os.path.join(d, "targets.txt")
-        open(fn, "w").write("\\n".join(case["targets"]) + "\\n")
+        open(fn, "w").write("\n".join(case["targets"]) + "\n")
         args = case["args"].split()
         args[args.index("-f") + 1] = fn
         r = subprocess.run([CLI] + args + ["-q", "-t", "1"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
