@@ -221,9 +221,12 @@ struct GiantParams {
   uint32_t pad;
   uint64_t n_steps;        // giant steps >= n_steps are outside the reference's walk and are skipped
 };
+#ifndef KH_GIANT_OUTLINE
+#define KH_GIANT_OUTLINE 0
+#endif
 struct GiantEmit {
   static constexpr bool NEED_Y = false;
-  static constexpr bool OUTLINE_MUL = false;
+  static constexpr bool OUTLINE_MUL = KH_GIANT_OUTLINE != 0;
   static constexpr bool PAIRS = true;
   KH_HDM void push(uint64_t batch, uint32_t idx) {
     uint32_t slot = kh_atomic_inc(gp.count);

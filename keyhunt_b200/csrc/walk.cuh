@@ -133,10 +133,9 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
         fe dyp, dym, sp, sm, xp, xm, c;
         fe_sub(dyp, gy, py);
         fe_add(dym, gy, py);
-        fe_mul(sp, dyp, dinv);
-        fe_mul(sm, dym, dinv);
-        fe_sqr(xp, sp);
-        fe_sqr(xm, sm);
+        fe_mul_sel<OL>(sp, dyp, dinv);
+        fe_mul_sel<OL>(sm, dym, dinv);
+        if (OL) { fe_mul_sel<true>(xp, sp, sp); fe_mul_sel<true>(xm, sm, sm); } else { fe_sqr(xp, sp); fe_sqr(xm, sm); }
         fe_add(c, px, gx);
         fe_sub(xp, xp, c);
         fe_sub(xm, xm, c);

@@ -8,6 +8,9 @@ from _oracle import Oracle
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 o = Oracle()
 kh = K.KeyHunt(0)
+import os
+if os.environ.get('KH_TPS'):
+    kh.set_option('threads_per_sm', int(os.environ['KH_TPS']))
 t0 = time.time()
 kh.bsgs_build(1 << 44, k)
 build_wall = time.time() - t0
