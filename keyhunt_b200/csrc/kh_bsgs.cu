@@ -410,7 +410,16 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
 
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
-  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+  wp.T = T; wp.n_batches = n_batches; wp.pad = 0;
+  // a found key ends the search (keyhunt.cpp:4644 `bsgs_found[k] == 0`): keep one launch to about 2^29 giant steps
+  // (~50 ms) so that the check between launches is fine-grained
+  {
+    const uint64_t per_step = T * (uint64_t)KH_GRP;
+    uint64_t steps = ((1ULL << 29) + per_step - 1) / per_step;
+    if (steps < 1) steps = 1;
+    if (steps > (uint64_t)c->steps_per_launch) steps = (uint64_t)c->steps_per_launch;
+    wp.steps = (uint32_t)steps;
+  }
 
   int result = KH_OK;
   uint64_t steps_done = 0;

@@ -222,7 +222,7 @@ const char *kh_last_error(kh_ctx *c) { return c ? c->err.c_str() : "no context";
 int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
   if (!c || !name) return KH_EINVAL;
   if (!strcmp(name, "threads_per_sm")) {
-    if (value < 32 || value > 2048) return kh_fail(c, KH_EINVAL, "threads_per_sm out of range");
+    if (value < 32 || value > 32768) return kh_fail(c, KH_EINVAL, "threads_per_sm out of range");
     c->threads_per_sm = (int)value;
   } else if (!strcmp(name, "steps_per_launch")) {
     if (value < 1 || value > (1 << 20)) return kh_fail(c, KH_EINVAL, "steps_per_launch out of range");

@@ -114,7 +114,7 @@ def test_multi_launch_and_tail(kh, oracle):
         assert got == sorted(set(idxs))
     finally:
         kh.set_option("steps_per_launch", 16)
-        kh.set_option("threads_per_sm", 512)
+        kh.set_option("threads_per_sm", 4096)
 
 
 def test_empty_and_duplicate_targets(kh, oracle):

@@ -16,7 +16,7 @@ for tp in tps:
     kh.set_option("threads_per_sm", tp)
     for name, mode, crypto, search in cases:
         kh.set_targets(mode, recs, crypto=crypto, search=search)
-        n = 1 << (31 if name == "xpoint" else 30)
+        n = 1 << (33 if name == "xpoint" else 32)
         kh.scan(0x4000000000000000, 1 << 26)  # warm
         kh.stats(reset=True)
         t0 = time.time()
