@@ -15,9 +15,11 @@
 
 using namespace kh;
 
+#ifndef KH_BLOCK
 #define KH_BLOCK 256
+#endif
 #ifndef KH_SCAN_MINBLOCKS
-#define KH_SCAN_MINBLOCKS 2
+#define KH_SCAN_MINBLOCKS (512 / KH_BLOCK)
 #endif
 
 // ---------------------------------------------------------------------------------------------------
