@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """Quick throughput probe of every scan kind (device-timed walk only)."""
-import random, sys, time
+import os, random, sys, time
+import numpy as np
 sys.path.insert(0, ".")
 import keyhunt_b200 as K
 
 kh = K.KeyHunt(0)
 print(kh.device_info())
 rnd = random.Random(1)
-recs = b"".join(rnd.randbytes(20) for _ in range(1024))
+ntg = int(os.environ.get("KH_NTG", "1024"))  # target-set size: 1024 = L1-resident bloom, 1e6 = L2, 5e7 = HBM
+recs = np.random.default_rng(1).integers(0, 256, size=ntg * 20, dtype=np.uint8).tobytes()
+print("targets", ntg)
 cases = [("xpoint", K.MODE_XPOINT, K.CRYPTO_BTC, K.SEARCH_COMPRESS), ("comp", K.MODE_RMD160, K.CRYPTO_BTC, K.SEARCH_COMPRESS),
          ("uncomp", K.MODE_RMD160, K.CRYPTO_BTC, K.SEARCH_UNCOMPRESS), ("both", K.MODE_RMD160, K.CRYPTO_BTC, K.SEARCH_BOTH),
          ("eth", K.MODE_ADDRESS, K.CRYPTO_ETH, K.SEARCH_COMPRESS)]
