@@ -40,7 +40,9 @@ int kh_create(kh_ctx **out, int device_ordinal);
 void kh_destroy(kh_ctx *ctx);
 const char *kh_last_error(kh_ctx *ctx);
 /* options: "threads_per_sm" (walker threads per SM), "steps_per_launch", "hit_capacity",
- * "endomorphism" (1 = the reference's -e: also test beta*x and beta^2*x of every point, keyhunt.cpp:3408-3473) */
+ * "endomorphism" (1 = the reference's -e: also test beta*x and beta^2*x of every point, keyhunt.cpp:3408-3473),
+ * "bsgs_base_check" (1 = kh_bsgs_search behaves like the reference SERVER's loop, which also reports a key equal to
+ *  the base key of a 2N window, bsgsd.cpp:2544; 0 = keyhunt.cpp's thread_process_bsgs, the default) */
 int kh_set_option(kh_ctx *ctx, const char *name, int64_t value);
 
 /* bloom_init2 sizing (bloom/bloom.cpp:154-187) with error = 0.000001 (keyhunt.cpp:7620) */

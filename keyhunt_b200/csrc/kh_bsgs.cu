@@ -94,7 +94,8 @@ struct RefineParams {
   const uint32_t *aux;      // AMP2 | AMP3
   const GiantCand *cands;
   uint32_t n_cands;
-  uint32_t pad;
+  uint32_t base_check;      // server variant: a window's base point equal to the target is a hit (bsgsd.cpp:2544)
+  uint64_t steps_per_window;// giant steps between window bases (= aux)
   ge q;                     // target public key
   u256 start;               // range start (base key of window 0)
   uint32_t *found;          // [0] flag
@@ -137,6 +138,17 @@ __global__ void __launch_bounds__(32) kh_refine_kernel(RefineParams rp) {
   u256_set_u64(two_m, rp.bt.m);
   { u256 z; u256_set_u64(z, 0); u256_add_mul64(two_m, z, two_m, 2); }
   u256_add_mul64(base2, rp.start, two_m, g);
+  // The reference's BSGS server compares base_key*G with the target before it walks a window (bsgsd.cpp:2528-2563).
+  // That case is giant step 0 of the window meeting baby step m (Q - (base+m)G = -mG), so it always arrives here as a
+  // tier-1 positive; the checks below cannot confirm it (they do not see offsets 0..2m of a window), this one does.
+  if (rp.base_check && (g % rp.steps_per_window) == 0) {
+    ge bp;
+    ge_mul_g(bp, base2);
+    if (!bp.inf && fe_eq(bp.x, rp.q.x) && fe_eq(bp.y, rp.q.y)) {
+      if (lane == 0 && atomicCAS(rp.found, 0u, 1u) == 0u) *rp.found_key = base2;
+      return;
+    }
+  }
   ge S;
   q_minus_key(S, rp.q, base2);
   // tier 2: lane i2 tests S + AMP2[i2]
@@ -405,7 +417,7 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
   GiantParams gp;
   gp.tier1 = bt.tier[0]; gp.cands = d_cands; gp.count = d_cnt; gp.cap = cap; gp.pad = 0; gp.n_steps = n_steps;
   RefineParams rp;
-  rp.bt = bt; rp.aux = c->d_aux_tab; rp.cands = d_cands; rp.n_cands = 0; rp.pad = 0;
+  rp.bt = bt; rp.aux = c->d_aux_tab; rp.cands = d_cands; rp.n_cands = 0; rp.base_check = (uint32_t)c->bsgs_base_check; rp.steps_per_window = d.aux;
   rp.q = ws.q; rp.start = start; rp.found = d_cnt + 1; rp.found_key = d_key;
 
   WalkParams wp;

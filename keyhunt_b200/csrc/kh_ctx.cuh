@@ -26,6 +26,7 @@ struct kh_ctx {
   int steps_per_launch = 16;
   uint32_t hit_capacity = 1u << 16;
   int endomorphism = 0;            // -e: test beta*x and beta^2*x of every point too
+  int bsgs_base_check = 0;         // server variant of the BSGS search (bsgsd.cpp:2544)
 
   // walk state
   uint64_t T_alloc = 0;            // walker threads the buffers are sized for

@@ -231,6 +231,8 @@ int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
     c->steps_per_launch = (int)value;
   } else if (!strcmp(name, "endomorphism")) {      // -e (FLAGENDOMORPHISM, keyhunt.cpp:924)
     c->endomorphism = value ? 1 : 0;
+  } else if (!strcmp(name, "bsgs_base_check")) {   // the reference SERVER's search loop (bsgsd.cpp:2544)
+    c->bsgs_base_check = value ? 1 : 0;
   } else if (!strcmp(name, "hit_capacity")) {
     if (value < 16 || value > (1 << 26)) return kh_fail(c, KH_EINVAL, "hit_capacity out of range");
     c->hit_capacity = (uint32_t)value;

@@ -456,8 +456,18 @@ static void dat_write(const std::string &fn, kh_ctx *c) {
   printf("........\n");
 }
 
+#ifdef KH_BSGSD
+#include "bsgsd_serve.hpp"
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 static void menu() {
+#ifdef KH_BSGSD
+  printf("\nUsage: keyhunt-b200-bsgsd [-k factor] [-n N] [-t gpus] [-i ip] [-p port] [-6]\n"
+         "GPU (B200) drop-in for keyhunt's bsgsd: builds (or reads) the BSGS tables once, keeps them in HBM and answers\n"
+         "\"<pubkey> <from>:<to>\" lines / HTTP POST JSON requests on ip:port (default 127.0.0.1:8080).\n");
+  exit(EXIT_FAILURE);
+#endif
   printf("\nUsage: keyhunt-b200 -m address|rmd160|xpoint|bsgs -f file [-r A:B | -b bits] [-l compress|uncompress|both] [-c btc|eth]\n"
          "                    [-k factor] [-n N] [-t gpus] [-I stride] [-s seconds] [-q] [-M] [-S] [-6] [-z mult]\n"
          "GPU (B200) drop-in for keyhunt's key-range search; same flags, -t selects the number of GPUs.\n");
@@ -475,8 +485,14 @@ int main(int argc, char **argv) {
   printf("[+] Version 0.2.230519 Satoshi Quest (keyhunt-b200: CUDA sm_100a back end)\n");
   const char *range_arg = nullptr, *str_stride = nullptr;
   int bitrange = 0, c, oi = 0;
+#ifdef KH_BSGSD
+  const char *listen_ip = "127.0.0.1";
+  int listen_port = 8080;
+  FLAGMODE = KH_MODE_BSGS;
+  FLAGSAVEREADFILE = 1;      // bsgsd always works from the .blm/.tbl files (bsgsd.cpp: FLAGSAVEREADFILE = 1)
+#endif
   stride_v = u_from_u64(1);
-  while ((c = getopt_long(argc, argv, "deh6MqRSB:b:c:C:E:f:I:k:l:m:N:n:p:r:s:t:v:G:8:z:", long_options, &oi)) != -1) {
+  while ((c = getopt_long(argc, argv, "deh6MqRSB:b:c:C:E:f:I:i:k:l:m:N:n:p:r:s:t:v:G:8:z:", long_options, &oi)) != -1) {
     switch (c) {
       case 0: fprintf(stderr, "[I] --%s accepted and ignored: bloom filters and the bP table are resident in GPU memory\n", long_options[oi].name); break;
       case 'h': menu(); break;
@@ -509,7 +525,13 @@ int main(int argc, char **argv) {
       case 's': OUTPUTSECONDS = atoi(optarg); if (OUTPUTSECONDS < 0) OUTPUTSECONDS = 30; if (!OUTPUTSECONDS) printf("[+] Turn off stats output\n"); else printf("[+] Stats output every %d seconds\n", OUTPUTSECONDS); break;
       case 't': NGPUS = atoi(optarg); if (NGPUS <= 0) NGPUS = 1; printf("[+] GPUs : %d\n", NGPUS); break;
       case 'z': FLAGBLOOMMULTIPLIER = atoi(optarg); if (FLAGBLOOMMULTIPLIER <= 0) FLAGBLOOMMULTIPLIER = 1; printf("[+] Bloom Size Multiplier %i\n", FLAGBLOOMMULTIPLIER); break;
-      case 'd': case 'v': case 'C': case 'E': case 'N': case 'p': case 'G': case '8': break;   // accepted, no effect here
+#ifdef KH_BSGSD
+      case 'p': listen_port = atoi(optarg); break;
+      case 'i': listen_ip = optarg; break;
+#else
+      case 'p': case 'i': break;
+#endif
+      case 'd': case 'v': case 'C': case 'E': case 'N': case 'G': case '8': break;   // accepted, no effect here
       default: menu();
     }
   }
@@ -544,7 +566,11 @@ int main(int argc, char **argv) {
     n_range_end = (bitrange == 256) ? order : u_shl1(n_range_start);
     if (u_cmp(n_range_end, order) > 0) n_range_end = order;
   } else {
+#ifdef KH_BSGSD
+    n_range_start = u_from_u64(1); n_range_end = order;   // every request carries its own range
+#else
     die("[E] a range is required: -r A:B or -b bits (random start needs the OS RNG and is not reproducible)");
+#endif
   }
 
   int ndev = NGPUS;
@@ -605,6 +631,7 @@ int main(int argc, char **argv) {
     // ---- BSGS ----------------------------------------------------------------------------------------
     std::vector<std::vector<uint8_t>> pubs;   // 64-byte X||Y
     std::vector<bool> pub_compressed;
+#ifndef KH_BSGSD
     FILE *f = fopen(fileName, "rb");
     if (!f) { fprintf(stderr, "[E] Can't open file %s\n", fileName); exit(EXIT_FAILURE); }
     printf("[+] Opening file %s\n", fileName);
@@ -624,6 +651,7 @@ int main(int argc, char **argv) {
     if (pubs.empty()) die("[E] The file don't have any valid publickeys");
     printf("[+] Added %zu points from file\n", pubs.size());
     printf("[+] Range \n[+] -- from : 0x%s\n[+] -- to   : 0x%s\n", u_hex(n_range_start).c_str(), u_hex(n_range_end).c_str());
+#endif
     kh_bsgs_desc d;
     // build (or load with -S) on every GPU: each holds its own replica of the tables
     for (size_t g = 0; g < gpus.size(); g++) {
@@ -641,6 +669,14 @@ int main(int argc, char **argv) {
         else if (g == 0) bsgs_save(gpus[g], d);
       }
     }
+#ifdef KH_BSGSD
+    {
+      for (kh_ctx *g : gpus) kh_set_option(g, "bsgs_base_check", 1);
+      const int rc = bsgsd_serve(gpus, d, listen_ip, listen_port);
+      for (kh_ctx *g : gpus) kh_destroy(g);
+      return rc;
+    }
+#endif
     // windows of 2N keys are dealt to GPUs in contiguous blocks; each key is searched until found
     const U256 two_n = u_mul_u64(u_from_u64(d.n), 2);
     std::vector<int> found(pubs.size(), 0);

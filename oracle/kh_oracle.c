@@ -987,6 +987,14 @@ static int bsgs_secondcheck(obsgs *b, const ge *Q, const fe *start_range, uint64
 
 int kho_bsgs_search(void *h, const uint8_t pub_xy[64], const uint8_t start_be[32], const uint8_t end_be[32],
                     uint8_t found_key[32], uint64_t *giant_steps, uint64_t *tier1_positives) {
+  return kho_bsgs_search_ex(h, pub_xy, start_be, end_be, 0, found_key, giant_steps, tier1_positives);
+}
+
+/* base_check != 0: the server variant of the loop (bsgsd.cpp:2528-2563) first compares every window's base point
+ * with the target, which finds a key equal to a window base (the giant-step path itself cannot see offsets 0..2m
+ * of a window) */
+int kho_bsgs_search_ex(void *h, const uint8_t pub_xy[64], const uint8_t start_be[32], const uint8_t end_be[32], int base_check,
+                       uint8_t found_key[32], uint64_t *giant_steps, uint64_t *tier1_positives) {
   obsgs *b = (obsgs *)h;
   ge Q; ge_from_be(&Q, pub_xy);
   fe base_key, end, step;
@@ -1003,6 +1011,11 @@ int kho_bsgs_search(void *h, const uint8_t pub_xy[64], const uint8_t start_be[32
     u256_set_u64(&t, 1025); u256_mul_u64(&t, &t, b->m);
     u256_sub(&km, &km, &t);
     ge aux, c, next;
+    if (base_check) {                                                            /* bsgsd.cpp:2544 base_point.equals */
+      ge bp;
+      ge_scalar_mul(&bp, &GE_G, &base_key);
+      if (u256_cmp(&bp.x, &Q.x) == 0 && u256_cmp(&bp.y, &Q.y) == 0) { fe_to_be(found_key, &base_key); found = 1; break; }
+    }
     ge_scalar_mul(&aux, &GE_G, &km);
     ge_add_direct(&c, &Q, &aux);
     for (uint64_t j = 0; j < cycles && !found; j++) {

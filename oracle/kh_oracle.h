@@ -98,6 +98,11 @@ const kho_bp_entry *kho_bsgs_table(void *b);            /* m3 entries, ascending
 int kho_bsgs_search(void *b, const uint8_t pub_xy[64], const uint8_t start[32], const uint8_t end[32],
                     uint8_t found_key[32], uint64_t *giant_steps, uint64_t *tier1_positives);
 
+/* the same loop as the reference's BSGS server runs it (bsgsd.cpp:2462): base_check != 0 adds the base-point
+ * comparison of bsgsd.cpp:2544 in front of every window */
+int kho_bsgs_search_ex(void *b, const uint8_t pub_xy[64], const uint8_t start[32], const uint8_t end[32], int base_check,
+                       uint8_t found_key[32], uint64_t *giant_steps, uint64_t *tier1_positives);
+
 #ifdef __cplusplus
 }
 #endif

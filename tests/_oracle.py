@@ -168,6 +168,8 @@ class Oracle(_Lib):
         self._sig("bsgs_table", C.POINTER(BpEntry), [C.c_void_p])
         self._sig("bsgs_search", C.c_int, [C.c_void_p, u8p, u8p, u8p, u8p, C.POINTER(C.c_uint64),
                                            C.POINTER(C.c_uint64)])
+        self._sig("bsgs_search_ex", C.c_int, [C.c_void_p, u8p, u8p, u8p, C.c_int, u8p, C.POINTER(C.c_uint64),
+                                              C.POINTER(C.c_uint64)])
 
     def ripemd160(self, data: bytes):
         o = C.create_string_buffer(20); self._ripemd160(data, len(data), o); return o.raw
@@ -225,10 +227,10 @@ class Oracle(_Lib):
         m3 = self.bsgs_params(b)["m3"]
         return C.string_at(self._bsgs_table(b), m3 * 16)
 
-    def bsgs_search(self, b, pub, start, end):
+    def bsgs_search(self, b, pub, start, end, base_check=False):
         o = C.create_string_buffer(32)
         gs, pos = C.c_uint64(), C.c_uint64()
-        r = self._bsgs_search(b, be32(pub[0]) + be32(pub[1]), be32(start), be32(end), o, C.byref(gs), C.byref(pos))
+        r = self._bsgs_search_ex(b, be32(pub[0]) + be32(pub[1]), be32(start), be32(end), int(base_check), o, C.byref(gs), C.byref(pos))
         return (int.from_bytes(o.raw, "big") if r else None), gs.value, pos.value
 
 

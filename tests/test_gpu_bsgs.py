@@ -111,3 +111,32 @@ def test_c4_full_size_properties(kh, oracle):
         assert kh.bsgs_search(oracle.pubkey(key), lo, hi) == key
     st = kh.stats()
     assert st["tier1_positives"] > 0
+
+
+def test_bsgs_server_variant_base_check(kh, oracle):
+    """option "bsgs_base_check" = the reference SERVER's loop (bsgsd.cpp:2544): a key equal to the base of a 2N window
+    is reported; without it (keyhunt.cpp's loop) the same key stays unseen.  Both against the oracle's two variants."""
+    n, k = 1 << 24, 4
+    kh.bsgs_build(n, k)
+    b = oracle.bsgs_new(n, k)
+    try:
+        m = oracle.bsgs_params(b)["m"]
+        start = 0x8000000001
+        end = start + 6 * 2 * n
+        keys = [start, start + 2 * n, start + 5 * 2 * n, start + 6 * 2 * n, start + 1, start + m, start + 2 * m, start + 2 * m + 1,
+                start + 2 * n - 1, start + 2 * n + 1, start + 3 * 2 * n + 12345]
+        try:
+            for flag in (0, 1):
+                kh.set_option("bsgs_base_check", flag)
+                for key in keys:
+                    pub = oracle.pubkey(key)
+                    want = oracle.bsgs_search(b, pub, start, end, base_check=bool(flag))[0]
+                    assert kh.bsgs_search(pub, start, end) == want, (flag, hex(key))
+            kh.set_option("bsgs_base_check", 1)
+            assert kh.bsgs_search(oracle.pubkey(start + 2 * n), start, end) == start + 2 * n
+            kh.set_option("bsgs_base_check", 0)
+            assert kh.bsgs_search(oracle.pubkey(start + 2 * n), start, end) == oracle.bsgs_search(b, oracle.pubkey(start + 2 * n), start, end)[0]
+        finally:
+            kh.set_option("bsgs_base_check", 0)
+    finally:
+        oracle.bsgs_free(b)
