@@ -14,7 +14,9 @@
 //
 // Deliberate differences (both are crashes or footguns of the reference, not behaviour a client can use):
 //  * a malformed public key gets "400 Bad Request" (the reference's ParsePublicKeyHex exits the whole server);
-//  * the default listen address is 127.0.0.1 as BSGSD.md documents (the reference binary binds 0.0.0.0).
+//  * the default listen address is 127.0.0.1 as BSGSD.md documents (the reference binary binds 0.0.0.0);
+//  * the table files are read / written only with -S (the reference server always does): rebuilding in HBM is faster
+//    than reading them back.
 #pragma once
 #include <arpa/inet.h>
 #include <netinet/in.h>

@@ -463,9 +463,10 @@ static void dat_write(const std::string &fn, kh_ctx *c) {
 // ---------------------------------------------------------------------------------------------------
 static void menu() {
 #ifdef KH_BSGSD
-  printf("\nUsage: keyhunt-b200-bsgsd [-k factor] [-n N] [-t gpus] [-i ip] [-p port] [-6]\n"
+  printf("\nUsage: keyhunt-b200-bsgsd [-k factor] [-n N] [-t gpus] [-i ip] [-p port] [-S] [-6]\n"
          "GPU (B200) drop-in for keyhunt's bsgsd: builds (or reads) the BSGS tables once, keeps them in HBM and answers\n"
-         "\"<pubkey> <from>:<to>\" lines / HTTP POST JSON requests on ip:port (default 127.0.0.1:8080).\n");
+         "\"<pubkey> <from>:<to>\" lines / HTTP POST JSON requests on ip:port (default 127.0.0.1:8080).\n"
+         "-S reads / writes the reference's keyhunt_bsgs_*.blm / .tbl files (the reference server always does).\n");
   exit(EXIT_FAILURE);
 #endif
   printf("\nUsage: keyhunt-b200 -m address|rmd160|xpoint|bsgs -f file [-r A:B | -b bits] [-l compress|uncompress|both] [-c btc|eth]\n"
@@ -489,7 +490,8 @@ int main(int argc, char **argv) {
   const char *listen_ip = "127.0.0.1";
   int listen_port = 8080;
   FLAGMODE = KH_MODE_BSGS;
-  FLAGSAVEREADFILE = 1;      // bsgsd always works from the .blm/.tbl files (bsgsd.cpp: FLAGSAVEREADFILE = 1)
+  // The reference server always reads/writes the .blm/.tbl files (bsgsd.cpp:238 FLAGSAVEREADFILE = 1).  Here the
+  // tables are rebuilt in HBM faster than a disk can deliver them (-k 4096: 62 GB in 18 s), so files are opt-in: -S.
 #endif
   stride_v = u_from_u64(1);
   while ((c = getopt_long(argc, argv, "deh6MqRSB:b:c:C:E:f:I:i:k:l:m:N:n:p:r:s:t:v:G:8:z:", long_options, &oi)) != -1) {

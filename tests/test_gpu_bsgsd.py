@@ -183,7 +183,7 @@ def test_servers_start_from_each_others_table_files(keys):
     names = ["keyhunt_bsgs_4_16384.blm", "keyhunt_bsgs_6_512.blm", "keyhunt_bsgs_7_16.blm", "keyhunt_bsgs_2_16.tbl"]
     q = keys[0x1234567][0] + b" 1000000:2000000\n"
     try:
-        g = Server(GPU_D, gdir); g.stop()            # writes the four files
+        g = Server(GPU_D, gdir, ["-S"]); g.stop()    # -S: writes the four files
         r = Server(REF_D, rdir, ["-6"]); r.stop()
         for n in names:
             a, b = open(os.path.join(gdir, n), "rb").read(), open(os.path.join(rdir, n), "rb").read()
@@ -197,7 +197,7 @@ def test_servers_start_from_each_others_table_files(keys):
             else:
                 body = lambda x: sorted(x[i:i + 16] for i in range(0, len(x) - 32, 16))   # the reference sort is not stable
                 assert body(a) == body(b), n
-        g2 = Server(GPU_D, rdir)                     # our server on the reference's files, checksums on
+        g2 = Server(GPU_D, rdir, ["-S"])             # our server on the reference's files, checksums on
         try:
             assert "Reading bP Table from file" in g2.text() and "Writing" not in g2.text()
             assert g2.ask(q) == b"1234567\n"
