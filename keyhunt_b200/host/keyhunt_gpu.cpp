@@ -9,7 +9,8 @@
 //
 //   -t N   number of GPUs to use (the reference's worker-thread count); default 1
 // Modes outside the GPU path (vanity, minikeys, pub2rmd), -R random and the mmap'd bloom/ptable flags are
-// parsed; the former are refused, the latter accepted and ignored (tables live in HBM).  -e is supported.
+// parsed; the former are refused, the latter accepted and ignored (tables live in HBM).  -e is supported;
+// -B sequential | backward | both are the window pickers over kh_bsgs_search.
 #include <getopt.h>
 #include <inttypes.h>
 #include <math.h>
@@ -21,6 +22,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -198,7 +200,7 @@ static bool decompress_pub(const uint8_t x_be[32], int odd, uint8_t y_be[32]) {
 // ---------------------------------------------------------------------------------------------------
 static int FLAGMODE = KH_MODE_ADDRESS, FLAGCRYPTO = 0, FLAGSEARCH = KH_SEARCH_BOTH, NGPUS = 1, KFACTOR = 1;
 static int FLAGQUIET = 0, FLAGMATRIX = 0, FLAGSAVEREADFILE = 0, FLAGSKIPCHECKSUM = 0, FLAGBITRANGE = 0, FLAGRANGE = 0, FLAG_N = 0;
-static int FLAGBLOOMMULTIPLIER = 1, OUTPUTSECONDS = 30, FLAGENDOMORPHISM = 0;
+static int FLAGBLOOMMULTIPLIER = 1, OUTPUTSECONDS = 30, FLAGENDOMORPHISM = 0, FLAGBSGSMODE = 0;
 static const char *fileName = "addresses.txt", *str_N = nullptr;
 static U256 n_range_start, n_range_end, stride_v;
 static uint64_t N_SEQUENTIAL_MAX = 0x100000000ULL;
@@ -504,7 +506,12 @@ int main(int argc, char **argv) {
       case 'S': FLAGSAVEREADFILE = 1; break;
       case 'R': die("[E] -R (random mode) uses the OS RNG and is not reproducible; not supported by the GPU back end");
       case 'e': FLAGENDOMORPHISM = 1; printf("[+] Endomorphism enabled\n"); break;
-      case 'B': if (strcmp(optarg, "sequential")) die("[E] only -B sequential is supported (got %s)", optarg); break;
+      case 'B':   // bsgs_modes keyhunt.cpp:423; random / dance draw from the OS RNG, ggsb / angrygiant re-order one window's giant steps
+        if (!strcmp(optarg, "sequential")) FLAGBSGSMODE = 0;
+        else if (!strcmp(optarg, "backward")) FLAGBSGSMODE = 1;
+        else if (!strcmp(optarg, "both")) FLAGBSGSMODE = 2;
+        else die("[E] -B %s is not supported by the GPU back end (sequential, backward, both)", optarg);
+        break;
       case 'b': bitrange = atoi(optarg); if (bitrange > 0 && bitrange <= 256) FLAGBITRANGE = 1; else fprintf(stderr, "[E] invalid bits param: %s.\n", optarg); break;
       case 'c': if (!strcmp(optarg, "btc")) FLAGCRYPTO = KH_CRYPTO_BTC; else if (!strcmp(optarg, "eth")) { FLAGCRYPTO = KH_CRYPTO_ETH; printf("[+] Setting search for ETH adddress.\n"); } else die("[E] Unknow crypto value %s", optarg); break;
       case 'f': fileName = optarg; break;
@@ -548,7 +555,7 @@ int main(int argc, char **argv) {
     printf("[+] Stride : %s\n", str_stride);
   }
   if (FLAGMODE == KH_MODE_ADDRESS && FLAGCRYPTO == 0) { FLAGCRYPTO = KH_CRYPTO_BTC; printf("[+] Setting search for btc adddress\n"); }
-  if (FLAGMODE == KH_MODE_BSGS) printf("[+] Mode BSGS sequential\n");
+  if (FLAGMODE == KH_MODE_BSGS) printf("[+] Mode BSGS %s\n", FLAGBSGSMODE == 0 ? "sequential" : FLAGBSGSMODE == 1 ? "backward" : "both");
   if (FLAGMODE == KH_MODE_BSGS && FLAGENDOMORPHISM) die("[E] Endomorphism doesn't work with BSGS");
 
   // range (keyhunt.cpp:1221-1262, :854-873)
@@ -679,34 +686,62 @@ int main(int argc, char **argv) {
       return rc;
     }
 #endif
-    // windows of 2N keys are dealt to GPUs in contiguous blocks; each key is searched until found
+    // Window pickers (-B).  A segment {from, to} stands for the windows based at from, from+2N, ... while below `to`
+    // (what one kh_bsgs_search call walks); the pickers differ only in how the range is cut into segments:
+    //   sequential (thread_process_bsgs :4549)          windows aligned at the range start
+    //   backward   (thread_process_bsgs_backward :5953) windows aligned at the range END, taken downwards; a last one
+    //                                                   clipped to the range start when the width is not a multiple of 2N
+    //   both       (thread_process_bsgs_both :6211)     the reference flips rand()%2 between the two cursors per window; here
+    //                                                   the lower half of the windows comes from the bottom cursor and the
+    //                                                   upper half from the top one, one of the coverings it can produce
+    // Windows of a segment are dealt to the GPUs in contiguous blocks; each key is searched until found.
     const U256 two_n = u_mul_u64(u_from_u64(d.n), 2);
-    std::vector<int> found(pubs.size(), 0);
+    std::unique_ptr<std::atomic<int>[]> found(new std::atomic<int>[pubs.size()]);
+    for (size_t k = 0; k < pubs.size(); k++) found[k] = 0;
     std::atomic<int> nfound{0};
-    U256 width = u_sub(n_range_end, n_range_start);
-    // number of windows = ceil(width / 2N) (bounded to 2^62 here)
-    uint64_t windows = 0;
-    { U256 acc = u_zero(); while (u_cmp(acc, width) < 0 && windows < (1ULL << 40)) { acc = u_add(acc, two_n); windows++; } }
+    const U256 width = u_sub(n_range_end, n_range_start);
+    for (int i = 0; i < 16; i++) if (width.b[i]) die("[E] BSGS ranges wider than 2^128 keys are not supported");
+    unsigned __int128 w128 = 0;
+    for (int i = 16; i < 32; i++) w128 = (w128 << 8) | width.b[i];
+    const unsigned __int128 step128 = (unsigned __int128)2 * d.n;
+    if ((w128 + step128 - 1) / step128 > ((unsigned __int128)1 << 50)) die("[E] more than 2^50 BSGS windows in the range: raise -n / -k");
+    const uint64_t q_full = (uint64_t)(w128 / step128), windows = (uint64_t)((w128 + step128 - 1) / step128);
+    const bool ragged = (w128 % step128) != 0;
+    struct Seg { U256 from, to; uint64_t windows; };
+    std::vector<Seg> segs;
+    if (FLAGBSGSMODE == 0) segs.push_back({n_range_start, n_range_end, windows});
+    else if (FLAGBSGSMODE == 1) {
+      if (q_full) segs.push_back({u_sub(n_range_end, u_mul_u64(two_n, q_full)), n_range_end, q_full});
+      if (ragged) segs.push_back({n_range_start, u_add(n_range_start, u_from_u64(1)), 1});
+    } else {
+      const uint64_t bottom = (windows + 1) / 2, top = windows - bottom;
+      U256 bt = u_add(n_range_start, u_mul_u64(two_n, bottom));
+      if (u_cmp(bt, n_range_end) > 0) bt = n_range_end;
+      segs.push_back({n_range_start, bt, bottom});
+      if (top) segs.push_back({u_sub(n_range_end, u_mul_u64(two_n, top)), n_range_end, top});
+    }
     auto worker = [&](size_t g) {
-      const uint64_t base = windows / gpus.size(), rem = windows % gpus.size();
-      const uint64_t first = g * base + std::min<uint64_t>(g, rem), cnt = base + (g < rem ? 1 : 0);
-      if (!cnt) return;
-      U256 from = u_add(n_range_start, u_mul_u64(two_n, first));
-      U256 to = u_add(from, u_mul_u64(two_n, cnt));
-      if (u_cmp(to, n_range_end) > 0 && g + 1 == gpus.size()) to = n_range_end;
-      for (size_t k = 0; k < pubs.size(); k++) {
-        if (found[k]) continue;
-        uint8_t key[32]; int fnd = 0;
-        if (!FLAGQUIET) { printf("[+] Thread 0x%s \n", u_hex(from).c_str()); fflush(stdout); }
-        if (kh_bsgs_search(gpus[g], pubs[k].data(), from.b, to.b, key, &fnd) != KH_OK) die("[E] %s", kh_last_error(gpus[g]));
-        if (fnd) {
-          U256 kk; memcpy(kk.b, key, 32);
-          std::string pubhex = pub_compressed[k] ? (std::string((pubs[k][63] & 1) ? "03" : "02") + hex_of(pubs[k].data(), 32)) : ("04" + hex_of(pubs[k].data(), 64));
-          std::lock_guard<std::mutex> lk(write_keys);
-          printf("[+] Thread Key found privkey %s   \n[+] Publickey %s\n", u_hex(kk).c_str(), pubhex.c_str());
-          FILE *fk = fopen("KEYFOUNDKEYFOUND.txt", "a");
-          if (fk) { fprintf(fk, "Key found privkey %s\nPublickey %s\n", u_hex(kk).c_str(), pubhex.c_str()); fclose(fk); }
-          found[k] = 1; nfound++;
+      for (const Seg &sg : segs) {
+        const uint64_t base = sg.windows / gpus.size(), rem = sg.windows % gpus.size();
+        const uint64_t first = g * base + std::min<uint64_t>(g, rem), cnt = base + (g < rem ? 1 : 0);
+        if (!cnt) continue;
+        const U256 from = u_add(sg.from, u_mul_u64(two_n, first));
+        U256 to = u_add(from, u_mul_u64(two_n, cnt));
+        if (first + cnt == sg.windows) to = sg.to;                 // the last window of a segment keeps the reference's overshoot past `to`
+        for (size_t k = 0; k < pubs.size(); k++) {
+          if (found[k].load()) continue;
+          uint8_t key[32]; int fnd = 0;
+          if (!FLAGQUIET) { printf("[+] Thread 0x%s \n", u_hex(from).c_str()); fflush(stdout); }
+          if (kh_bsgs_search(gpus[g], pubs[k].data(), from.b, to.b, key, &fnd) != KH_OK) die("[E] %s", kh_last_error(gpus[g]));
+          if (fnd && !found[k].exchange(1)) {
+            U256 kk; memcpy(kk.b, key, 32);
+            std::string pubhex = pub_compressed[k] ? (std::string((pubs[k][63] & 1) ? "03" : "02") + hex_of(pubs[k].data(), 32)) : ("04" + hex_of(pubs[k].data(), 64));
+            std::lock_guard<std::mutex> lk(write_keys);
+            printf("[+] Thread Key found privkey %s   \n[+] Publickey %s\n", u_hex(kk).c_str(), pubhex.c_str());
+            FILE *fk = fopen("KEYFOUNDKEYFOUND.txt", "a");
+            if (fk) { fprintf(fk, "Key found privkey %s\nPublickey %s\n", u_hex(kk).c_str(), pubhex.c_str()); fclose(fk); }
+            nfound++;
+          }
         }
       }
     };

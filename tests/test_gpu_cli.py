@@ -149,3 +149,27 @@ def test_cli_target_cache_file_identical_and_interchangeable(dirs):
     rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "1"], r)   # -t 1: the reference checks the cursor outside its mutex, extra threads overshoot
     assert "Reading file data_" in out_g and "Reading file data_" in out_r
     assert records(g, 4) == want and records(r, 4) == want
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/keyhunt not built")
+@pytest.mark.parametrize("mode", ["sequential", "backward", "both"])
+def test_cli_bsgs_window_pickers_identical_to_reference(dirs, oracle, mode):
+    """-B sequential | backward | both (keyhunt.cpp:4549, :5953, :6211): same found keys as the reference, including the
+    keys that only one alignment of the 2N windows can see (just past the range end, at the range start)"""
+    g, r = dirs
+    inside = [0x1000002, 0x1234567, 0x17FFFFF, 0x1800000, 0x2800065, 0x8000000, 0x8FFFFFF]
+    edge = [0x1000001, 0x9000000, 0x9000001, 0x9000010, 0xFFFFFF]          # alignment-dependent or never found
+    keys = inside + ([] if mode == "both" else edge)                         # `both` picks its windows with rand() in the reference
+    lines = []
+    for k in keys:
+        x, y = oracle.pubkey(k)
+        lines.append(("03" if y & 1 else "02") + "%064x" % x)
+    for d in (g, r):
+        open(os.path.join(d, "p.txt"), "w").write("\n".join(lines) + "\n")
+    args = ["-m", "bsgs", "-f", "p.txt", "-n", "0x400000", "-k", "2", "-r", "1000001:9000000", "-q", "-B", mode]
+    rc_g, out_g = run(CLI, args + ["-t", "1"], g)
+    rc_r, out_r = run(REF_BIN, args + ["-s", "0", "-t", "2"], r)
+    assert rc_g == rc_r, (out_g[-1500:], out_r[-1500:])
+    assert records(g, 2) == records(r, 2), (records(g, 2), records(r, 2))
+    found = {int(rec.split("|")[0].split()[-1], 16) for rec in records(g, 2)}
+    assert set(inside) <= found
