@@ -42,7 +42,8 @@ WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
                start=0x1, n_targets=32, ops=5800, disp=2),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
-               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950, disp=1),
+               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950, disp=1,
+               alu_ops=7500),   # ncu: ALU-pipe thread instructions per point of kh_scan_kernel<BOTH> (profiles/r01_final_both_ncu_sections.txt)
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
                mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900, disp=1),
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
@@ -446,7 +447,13 @@ def main():
                      "peak_source": "measured live: kh_int_peak LOP3+IMAD dual-pipe rate; ALU pipe alone %.2f, IMAD %.2f, IMAD.WIDE %.2f Tiop/s"
                                     % (peaks["lop3"] / 1e12, peaks["imad"] / 1e12, peaks["imad_wide"] / 1e12),
                      "frac_of_nominal_64_lanes": achieved / nominal, "nominal_peak": nominal,
-                     "hbm_gbs_scratch": 32.0 * value * 1e6 / 1e9, "hbm_peak_gbs": mp.get("hbm_gbs")},
+                     "hbm_gbs_scratch": 32.0 * value * 1e6 / 1e9, "hbm_peak_gbs": mp.get("hbm_gbs"),
+                     # the pipe that actually binds (ncu: ALU 84 % busy, top stall math_pipe_throttle): ALU ops per point x points/s
+                     # against the live-measured ALU-only rate
+                     "binding_pipe": ({"pipe": "alu", "ops_per_point": w["alu_ops"],
+                                       "achieved": pts_per_launch * w["alu_ops"] / (launch_ms * 1e-3) / 1e12, "peak": peaks["lop3"] / 1e12,
+                                       "frac": pts_per_launch * w["alu_ops"] / (launch_ms * 1e-3) / peaks["lop3"], "unit": "Tiop/s"}
+                                      if "alu_ops" in w else None)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

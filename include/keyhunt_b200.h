@@ -29,7 +29,7 @@ extern "C" {
 typedef struct kh_ctx kh_ctx;
 
 /* FLAGMODE / FLAGCRYPTO / FLAGSEARCH values of the reference (keyhunt.cpp:55-68) */
-enum { KH_MODE_XPOINT = 0, KH_MODE_ADDRESS = 1, KH_MODE_BSGS = 2, KH_MODE_RMD160 = 3 };
+enum { KH_MODE_XPOINT = 0, KH_MODE_ADDRESS = 1, KH_MODE_BSGS = 2, KH_MODE_RMD160 = 3, KH_MODE_VANITY = 6 };
 enum { KH_CRYPTO_BTC = 1, KH_CRYPTO_ETH = 2 };
 enum { KH_SEARCH_UNCOMPRESS = 0, KH_SEARCH_COMPRESS = 1, KH_SEARCH_BOTH = 2 };
 /* which derived value matched */
@@ -62,6 +62,12 @@ int kh_bloom_params(uint64_t entries, kh_bloom_desc *out);
  * desc overrides it (keyhunt.cpp:7608). */
 int kh_set_targets(kh_ctx *ctx, int mode, int crypto, int search, const uint8_t *records20, uint64_t n_records,
                    const kh_bloom_desc *desc, const uint8_t *bloom_bits);
+/* -m vanity: replaces processOneVanity / readFileVanity (keyhunt.cpp:6971-7030) + vanityrmdmatch (:6677) inside
+ * thread_process_vanity (:3867).  The caller passes what addvanity (:6739) produced: n_pairs interval limits
+ * vanity_rmd_limit_values_A/B[i][j], flattened, 20 bytes each; a hash160 h matches when A <= h <= B (memcmp order) for
+ * some pair.  Candidates per point follow `search` exactly like -m rmd160 (both compressed prefixes / uncompressed),
+ * hits come back through kh_poll_hits with the same n-k fix-up, and "endomorphism" applies.  BTC only. */
+int kh_set_vanity(kh_ctx *ctx, int search, const uint8_t *limits_a20, const uint8_t *limits_b20, uint64_t n_pairs);
 /* read back the device-resident bloom image / sorted table (parity checks, -S style persistence) */
 int kh_get_bloom(kh_ctx *ctx, kh_bloom_desc *desc, uint8_t *dst, uint64_t cap_bytes);
 int kh_get_table(kh_ctx *ctx, uint8_t *dst20, uint64_t cap_records, uint64_t *n_records);

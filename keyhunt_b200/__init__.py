@@ -13,7 +13,7 @@ import ctypes as C
 import os
 
 __all__ = ["KeyHunt", "KhError", "Hit", "KeyInfo", "BloomDesc", "BsgsDesc", "Stats", "load_library", "LIB_PATH",
-           "MODE_XPOINT", "MODE_ADDRESS", "MODE_BSGS", "MODE_RMD160", "CRYPTO_BTC", "CRYPTO_ETH",
+           "MODE_XPOINT", "MODE_ADDRESS", "MODE_BSGS", "MODE_RMD160", "MODE_VANITY", "CRYPTO_BTC", "CRYPTO_ETH",
            "SEARCH_UNCOMPRESS", "SEARCH_COMPRESS", "SEARCH_BOTH",
            "HIT_COMP02", "HIT_COMP03", "HIT_UNCOMP", "HIT_ETH", "HIT_XPOINT", "N_ORDER", "parse_targets"]
 
@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("KH_B200_LIB") or os.path.join(_HERE, "libkh_b200.so")
 
 # keyhunt.cpp:76-90
 MODE_XPOINT, MODE_ADDRESS, MODE_BSGS, MODE_RMD160 = 0, 1, 2, 3
+MODE_VANITY = 6
 CRYPTO_BTC, CRYPTO_ETH = 1, 2
 SEARCH_UNCOMPRESS, SEARCH_COMPRESS, SEARCH_BOTH = 0, 1, 2
 HIT_COMP02, HIT_COMP03, HIT_UNCOMP, HIT_ETH, HIT_XPOINT = 0, 1, 2, 3, 4
@@ -30,7 +31,7 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 EXPORTS = ["kh_create", "kh_destroy", "kh_last_error", "kh_set_option", "kh_bloom_params", "kh_set_targets",
            "kh_get_bloom", "kh_get_table", "kh_scan", "kh_poll_hits", "kh_derive", "kh_bsgs_build",
            "kh_bsgs_describe", "kh_bsgs_export", "kh_bsgs_import", "kh_bsgs_search", "kh_get_stats",
-           "kh_device_info", "kh_int_peak"]
+           "kh_device_info", "kh_int_peak", "kh_set_vanity"]
 
 
 class KhError(RuntimeError):
@@ -201,6 +202,12 @@ class KeyHunt:
             raise ValueError("records20 must be a multiple of 20 bytes")
         self._ck(self._lib.kh_set_targets(self._h, mode, crypto, search, records20, len(records20) // 20,
                                           C.byref(desc) if desc is not None else None, bloom_bits))
+
+    def set_vanity(self, limits_a, limits_b, search=SEARCH_COMPRESS):
+        """-m vanity: limits_a / limits_b = N x 20 bytes, the interval pairs addvanity (keyhunt.cpp:6739) produced."""
+        if len(limits_a) != len(limits_b) or len(limits_a) % 20:
+            raise ValueError("limits must be two equal multiples of 20 bytes")
+        self._ck(self._lib.kh_set_vanity(self._h, search, limits_a, limits_b, len(limits_a) // 20))
 
     def get_bloom(self):
         d = BloomDesc()

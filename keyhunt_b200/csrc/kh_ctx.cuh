@@ -43,6 +43,8 @@ struct kh_ctx {
   uint32_t *d_table = nullptr;     // N x 5 BE words
   uint64_t n_targets = 0;
   std::vector<uint8_t> h_table20;  // sorted records (host copy for kh_get_table)
+  uint32_t *d_vanity = nullptr;    // -m vanity: prefix bitmap + interval limits (ScanTargets::van)
+  uint32_t n_vanity = 0;
 
   // hits
   kh::RawHit *d_hits = nullptr;

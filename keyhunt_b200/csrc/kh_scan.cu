@@ -11,16 +11,9 @@
 #include <algorithm>
 #include <numeric>
 
-#include "kh_ctx.cuh"
+#include "scan_kernel.cuh"
 
 using namespace kh;
-
-#ifndef KH_BLOCK
-#define KH_BLOCK 256
-#endif
-#ifndef KH_SCAN_MINBLOCKS
-#define KH_SCAN_MINBLOCKS (512 / KH_BLOCK)
-#endif
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
@@ -39,23 +32,6 @@ __global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *g
 #pragma unroll
     for (int l = 0; l < 8; l++) { centers[(uint64_t)l * ws.T + t] = cx.v[l]; centers[(uint64_t)(8 + l) * ws.T + t] = cy.v[l]; }
   }
-}
-
-__device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *gtab) {
-  const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
-  uint4 *dst = reinterpret_cast<uint4 *>(smem);
-  for (int i = threadIdx.x; i < KH_TAB_WORDS / 4; i += blockDim.x) dst[i] = src[i];
-  __syncthreads();
-}
-
-template <int KIND, bool ENDO>
-__global__ void __launch_bounds__(KH_BLOCK, KH_SCAN_MINBLOCKS) kh_scan_kernel(WalkParams wp, ScanTargets tg) {
-  extern __shared__ __align__(16) uint32_t kh_smem_tab[];
-  kh_stage_table(kh_smem_tab, wp.gtab);
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= wp.T) return;
-  ScanEmit<KIND, ENDO> emit(tg);
-  walk_batches(wp, kh_smem_tab, t, emit);
 }
 
 __global__ void kh_bloom_build(BloomDev bl, const uint32_t *table_be, uint64_t n) {
@@ -211,7 +187,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -318,7 +294,44 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
   KH_CUDA(c, cudaGetLastError());
   c->bloom_desc = d;
   c->n_targets = n;
+  c->n_vanity = 0;
   c->mode = mode; c->crypto = crypto; c->search = search; c->scan_kind = kind;
+  c->have_targets = true;
+  return KH_OK;
+}
+
+int kh_set_vanity(kh_ctx *c, int search, const uint8_t *a20, const uint8_t *b20, uint64_t n) {
+  if (!c) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  if (!a20 || !b20 || n == 0) return kh_fail(c, KH_EINVAL, "There aren't any vanity targets");
+  if (n > (1u << 20)) return kh_fail(c, KH_EINVAL, "too many vanity intervals");
+  int kind;
+  if (search == KH_SEARCH_COMPRESS) kind = KH_SCAN_COMP;
+  else if (search == KH_SEARCH_UNCOMPRESS) kind = KH_SCAN_UNCOMP;
+  else if (search == KH_SEARCH_BOTH) kind = KH_SCAN_BOTH;
+  else return kh_fail(c, KH_EINVAL, "bad search type %d", search);
+  std::vector<uint32_t> van(2048 + 10 * n, 0u);
+  auto pack = [](uint32_t *dst, const uint8_t *p) {
+    for (int k = 0; k < 5; k++) dst[k] = ((uint32_t)p[4 * k] << 24) | ((uint32_t)p[4 * k + 1] << 16) | ((uint32_t)p[4 * k + 2] << 8) | p[4 * k + 3];
+  };
+  for (uint64_t i = 0; i < n; i++) {
+    const uint8_t *a = a20 + 20 * i, *b = b20 + 20 * i;
+    pack(&van[2048 + 10 * i], a);
+    pack(&van[2048 + 10 * i + 5], b);
+    if (memcmp(a, b, 20) > 0) continue;                     // empty interval: nothing can match it
+    const uint32_t pa = ((uint32_t)a[0] << 8) | a[1], pb = ((uint32_t)b[0] << 8) | b[1];
+    for (uint32_t p = pa; p <= pb; p++) van[p >> 5] |= 1u << (p & 31);
+  }
+  if (c->d_vanity) { cudaFree(c->d_vanity); c->d_vanity = nullptr; }
+  c->have_targets = false;
+  KH_CUDA(c, cudaMalloc(&c->d_vanity, van.size() * sizeof(uint32_t)));
+  KH_CUDA(c, cudaMemcpyAsync(c->d_vanity, van.data(), van.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_vanity = (uint32_t)n;
+  c->n_targets = 0;
+  c->h_table20.clear();
+  memset(&c->bloom_desc, 0, sizeof(c->bloom_desc));
+  c->mode = KH_MODE_VANITY; c->crypto = KH_CRYPTO_BTC; c->search = search; c->scan_kind = kind;
   c->have_targets = true;
   return KH_OK;
 }
@@ -393,7 +406,9 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   if (rc) return rc;
 
   ScanTargets tg;
-  tg.bloom.bf = c->d_bloom; tg.bloom.bits = c->bloom_desc.bits; tg.bloom.magic = (~0ULL) / c->bloom_desc.bits;
+  const bool vanity = (c->mode == KH_MODE_VANITY);
+  tg.van = vanity ? c->d_vanity : nullptr; tg.van_n = vanity ? c->n_vanity : 0u; tg.van_pad = 0;
+  tg.bloom.bf = c->d_bloom; tg.bloom.bits = c->bloom_desc.bits; tg.bloom.magic = vanity ? 0ull : (~0ULL) / c->bloom_desc.bits;
   tg.bloom.stride = 0; tg.bloom.hashes = c->bloom_desc.hashes; tg.bloom.pad = 0;
   tg.table = c->d_table; tg.n = c->n_targets;
   tg.sink.hits = c->d_hits; tg.sink.count = c->d_hit_count; tg.sink.cap = c->hits_alloc; tg.sink.pad = 0;
@@ -407,7 +422,8 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
     wp.batch_base = base;
     cudaError_t e;
-    switch (c->scan_kind) {
+    if (vanity) e = kh_launch_vanity(c, c->scan_kind, wp, tg);
+    else switch (c->scan_kind) {
       case KH_SCAN_XPOINT: e = launch_scan<KH_SCAN_XPOINT>(c, wp, tg); break;
       case KH_SCAN_COMP: e = launch_scan<KH_SCAN_COMP>(c, wp, tg); break;
       case KH_SCAN_UNCOMP: e = launch_scan<KH_SCAN_UNCOMP>(c, wp, tg); break;

@@ -1,0 +1,32 @@
+// scan_kernel.cuh — the scan kernel template, shared by kh_scan.cu (table searches) and kh_vanity.cu (-m vanity
+// instantiations, a separate translation unit so that the two compile in parallel).
+#pragma once
+#include "kh_ctx.cuh"
+
+#ifndef KH_BLOCK
+#define KH_BLOCK 256
+#endif
+// two CTAs of 256 threads per SM (128 registers per thread)
+#ifndef KH_SCAN_MINBLOCKS
+#define KH_SCAN_MINBLOCKS (512 / KH_BLOCK)
+#endif
+
+__device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *gtab) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
+  uint4 *dst = reinterpret_cast<uint4 *>(smem);
+  for (int i = threadIdx.x; i < KH_TAB_WORDS / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+template <int KIND, bool ENDO, bool VANITY = false>
+__global__ void __launch_bounds__(KH_BLOCK, KH_SCAN_MINBLOCKS) kh_scan_kernel(kh::WalkParams wp, kh::ScanTargets tg) {
+  extern __shared__ __align__(16) uint32_t kh_smem_tab[];
+  kh_stage_table(kh_smem_tab, wp.gtab);
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= wp.T) return;
+  kh::ScanEmit<KIND, ENDO, VANITY> emit(tg);
+  kh::walk_batches(wp, kh_smem_tab, t, emit);
+}
+
+// kh_vanity.cu: launches kh_scan_kernel<KIND, endo, true> for KIND = COMP / UNCOMP / BOTH
+cudaError_t kh_launch_vanity(kh_ctx *c, int kind, const kh::WalkParams &wp, const kh::ScanTargets &tg);

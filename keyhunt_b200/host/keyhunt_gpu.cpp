@@ -8,7 +8,7 @@
 // file checksums, and one modular square root per BSGS public key to decompress it).
 //
 //   -t N   number of GPUs to use (the reference's worker-thread count); default 1
-// Modes outside the GPU path (vanity, minikeys, pub2rmd), -R random and the mmap'd bloom/ptable flags are
+// Modes outside the GPU path (minikeys, pub2rmd), -R random and the mmap'd bloom/ptable flags are
 // parsed; the former are refused, the latter accepted and ignored (tables live in HBM).  -e is supported;
 // -B sequential | backward | both are the window pickers over kh_bsgs_search.
 #include <getopt.h>
@@ -256,6 +256,73 @@ static std::vector<uint8_t> load_targets(const char *fn) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// -m vanity targets: addvanity (keyhunt.cpp:6739-6860).  A base58 prefix becomes one [A, B] interval of hash160 values per
+// address length it can have: the prefix is padded with '1' (lowest digit) for A and with 'z' (highest) for B until the
+// decode is 25 bytes long, and bytes 1..20 of each 25-byte decode are the limits.
+// ---------------------------------------------------------------------------------------------------
+static std::vector<uint8_t> vanity_A, vanity_B;      // flattened 20-byte limits, pair i = [A_i, B_i]
+static int vanity_targets = 0;
+// the reference decoder's conventions (base58/base58.c:39): the value fills a binsz-byte big-endian buffer; the reported
+// length is (bytes after the leading zero bytes) + (number of leading '1' digits); false = bad digit / does not fit
+static bool b58_fixed(const std::string &t, size_t binsz, std::vector<uint8_t> &bin, size_t &reported) {
+  bin.assign(binsz, 0);
+  size_t i = 0, ones = 0;
+  while (i < t.size() && t[i] == '1') { ones++; i++; }
+  for (; i < t.size(); i++) {
+    const char *d = strchr(B58, t[i]);
+    if (!d || !t[i]) return false;
+    unsigned carry = (unsigned)(d - B58);
+    for (size_t j = binsz; j-- > 0;) { unsigned v = bin[j] * 58u + carry; bin[j] = (uint8_t)v; carry = v >> 8; }
+    if (carry) return false;
+  }
+  size_t lead = 0;
+  while (lead < binsz && !bin[lead]) lead++;
+  reported = binsz - lead + ones;
+  return true;
+}
+static std::vector<std::vector<uint8_t>> vanity_limits(const std::string &prefix, char fill) {
+  std::vector<std::vector<uint8_t>> out;
+  std::string t = prefix;
+  std::vector<uint8_t> bin;
+  for (;;) {
+    size_t len = 50;
+    if (!b58_fixed(t, 50, bin, len)) len = 50;             // a failed decode leaves the length at 50 and ends the loop (:6767)
+    if (len > 25 || t.size() > 48) break;
+    if (len == 25) {
+      size_t l2;
+      b58_fixed(t, 25, bin, l2);                            // decoded again into exactly 25 bytes: version | hash160 | checksum
+      out.emplace_back(bin.begin() + 1, bin.begin() + 21);
+    }
+    t.push_back(fill);
+  }
+  return out;
+}
+static bool is_b58_string(const std::string &s) { for (char ch : s) if (!ch || !strchr(B58, ch)) return false; return true; }
+static int add_vanity(const std::string &target) {
+  if (target.size() >= 30) return 0;
+  auto a = vanity_limits(target, '1'), b = vanity_limits(target, 'z');
+  const size_t r = std::min(a.size(), b.size());
+  for (size_t j = 0; j < r; j++) { vanity_A.insert(vanity_A.end(), a[j].begin(), a[j].end()); vanity_B.insert(vanity_B.end(), b[j].begin(), b[j].end()); }
+  if (r) vanity_targets++;
+  return (int)r;
+}
+// readFileVanity (keyhunt.cpp:6990): one prefix per line; a missing file is fine when -v gave targets
+static void read_vanity_file(const char *fn) {
+  FILE *f = fopen(fn, "r");
+  if (f) {
+    char line[100];
+    while (fgets(line, sizeof(line), f)) {
+      std::string s = trim(line);
+      if (s.empty() || s.size() >= 36) continue;
+      if (is_b58_string(s)) add_vanity(s);
+      else fprintf(stderr, "[E] the string \"%s\" is not valid Base58, omiting it\n", s.c_str());
+    }
+    fclose(f);
+  }
+  if (vanity_targets == 0) { fprintf(stderr, "[E] There aren't any vanity targets\n[E] Unenexpected error\n"); exit(EXIT_FAILURE); }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // hit output (writekey keyhunt.cpp:6891, writekeyeth :6925)
 // ---------------------------------------------------------------------------------------------------
 static void write_scan_hit(kh_ctx *c, const kh_hit &h) {
@@ -276,6 +343,14 @@ static void write_scan_hit(kh_ctx *c, const kh_hit &h) {
     if (compressed) { pub = std::string((ki.pub_y[31] & 1) ? "03" : "02") + hex_of(ki.pub_x, 32); rmd = ki.h160_comp; }
     else { pub = "04" + hex_of(ki.pub_x, 32) + hex_of(ki.pub_y, 32); rmd = ki.h160_uncomp; }
     std::string addr = rmd160_to_address(rmd), hexrmd = hex_of(rmd, 20);
+    if (FLAGMODE == KH_MODE_VANITY) {                                                    // writevanitykey keyhunt.cpp:6705
+      if (keys) fclose(keys);
+      keys = fopen("VANITYKEYFOUND.txt", "a+");
+      if (keys) { fprintf(keys, "Vanity Private Key: %s\npubkey: %s\nAddress %s\nrmd160 %s\n", hexkey.c_str(), pub.c_str(), addr.c_str(), hexrmd.c_str()); fclose(keys); }
+      printf("\nVanity Private Key: %s\npubkey: %s\nAddress %s\nrmd160 %s\n", hexkey.c_str(), pub.c_str(), addr.c_str(), hexrmd.c_str());
+      fflush(stdout);
+      return;
+    }
     if (keys) { fprintf(keys, "Private Key: %s\npubkey: %s\nAddress %s\nrmd160 %s\n", hexkey.c_str(), pub.c_str(), addr.c_str(), hexrmd.c_str()); fclose(keys); }
     printf("\nHit! Private Key: %s\npubkey: %s\nAddress %s\nrmd160 %s\n", hexkey.c_str(), pub.c_str(), addr.c_str(), hexrmd.c_str());
   }
@@ -300,6 +375,7 @@ static void scan_worker(kh_ctx *c, int id) {
     do {
       int rc = kh_poll_hits(c, hits, 64, &n);
       if (rc != KH_OK && rc != KH_EOVERFLOW) die("[E] %s", kh_last_error(c));
+      if (rc == KH_EOVERFLOW) fprintf(stderr, "\n[W] more hits in the chunk at %s than the device hit buffer holds: the excess was DROPPED; use a smaller -n\n", u_hex(key).c_str());
       for (int i = 0; i < n; i++) write_scan_hit(c, hits[i]);
     } while (n == 64);
   }
@@ -471,7 +547,7 @@ static void menu() {
          "-S reads / writes the reference's keyhunt_bsgs_*.blm / .tbl files (the reference server always does).\n");
   exit(EXIT_FAILURE);
 #endif
-  printf("\nUsage: keyhunt-b200 -m address|rmd160|xpoint|bsgs -f file [-r A:B | -b bits] [-l compress|uncompress|both] [-c btc|eth]\n"
+  printf("\nUsage: keyhunt-b200 -m address|rmd160|xpoint|bsgs|vanity -f file [-v prefix] [-r A:B | -b bits] [-l compress|uncompress|both] [-c btc|eth]\n"
          "                    [-k factor] [-n N] [-t gpus] [-I stride] [-s seconds] [-q] [-M] [-S] [-6] [-z mult]\n"
          "GPU (B200) drop-in for keyhunt's key-range search; same flags, -t selects the number of GPUs.\n");
   exit(EXIT_FAILURE);
@@ -527,7 +603,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(optarg, "address")) { FLAGMODE = KH_MODE_ADDRESS; printf("[+] Mode address\n"); }
         else if (!strcmp(optarg, "bsgs")) { FLAGMODE = KH_MODE_BSGS; }
         else if (!strcmp(optarg, "rmd160")) { FLAGMODE = KH_MODE_RMD160; FLAGCRYPTO = KH_CRYPTO_BTC; printf("[+] Mode rmd160\n"); }
-        else die("[E] mode %s is not part of the GPU path (address, rmd160, xpoint, bsgs)", optarg);
+        else if (!strcmp(optarg, "vanity")) { FLAGMODE = KH_MODE_VANITY; printf("[+] Mode vanity\n"); }
+        else die("[E] mode %s is not part of the GPU path (address, rmd160, xpoint, bsgs, vanity)", optarg);
         break;
       case 'n': FLAG_N = 1; str_N = optarg; break;
       case 'r': range_arg = optarg; FLAGRANGE = 1; break;
@@ -540,7 +617,11 @@ int main(int argc, char **argv) {
 #else
       case 'p': case 'i': break;
 #endif
-      case 'd': case 'v': case 'C': case 'E': case 'N': case 'G': case '8': break;   // accepted, no effect here
+      case 'v':                                                                     // keyhunt.cpp:1083-1099
+        if (is_b58_string(optarg)) { if (add_vanity(optarg) > 0) printf("[+] Added Vanity search : %s\n", optarg); else printf("[+] Vanity search \"%s\" was NOT Added\n", optarg); }
+        else fprintf(stderr, "[+] The string \"%s\" is not Valid Base58\n", optarg);
+        break;
+      case 'd': case 'C': case 'E': case 'N': case 'G': case '8': break;   // accepted, no effect here
       default: menu();
     }
   }
@@ -605,9 +686,19 @@ int main(int argc, char **argv) {
     printf("[+] N = 0x%" PRIx64 "\n", N_SEQUENTIAL_MAX);
     if (FLAGBITRANGE) printf("[+] Bit Range %i\n", bitrange); else printf("[+] Range \n");
     printf("[+] -- from : 0x%s\n[+] -- to   : 0x%s\n", u_hex(n_range_start).c_str(), u_hex(n_range_end).c_str());
+    if (FLAGMODE == KH_MODE_VANITY) {
+      FLAGCRYPTO = KH_CRYPTO_BTC;
+      read_vanity_file(fileName);
+      for (kh_ctx *g : gpus) {
+        if (kh_set_option(g, "endomorphism", FLAGENDOMORPHISM) != KH_OK) die("[E] %s", kh_last_error(g));
+        if (kh_set_option(g, "hit_capacity", 1 << 22) != KH_OK) die("[E] %s", kh_last_error(g));   // short prefixes match often
+        if (kh_set_vanity(g, FLAGSEARCH, vanity_A.data(), vanity_B.data(), vanity_A.size() / 20) != KH_OK) die("[E] %s", kh_last_error(g));
+      }
+    }
     std::vector<uint8_t> recs, cached_bf;
     kh_bloom_desc d;
     bool from_cache = false;
+    if (FLAGMODE != KH_MODE_VANITY) {
     std::string cache = FLAGSAVEREADFILE ? dat_name(fileName) : std::string();
     if (FLAGSAVEREADFILE && dat_read(cache, d, cached_bf, recs)) from_cache = true;   // the reference's -S cache (bloom image reused bit for bit)
     else recs = load_targets(fileName);
@@ -625,6 +716,7 @@ int main(int argc, char **argv) {
     }
     if (FLAGSAVEREADFILE && !from_cache) dat_write(cache, gpus[0]);
     printf("[+] Sorting data ... done! %" PRIu64 " values were loaded and sorted\n", N);
+    }
     fflush(stdout);
     std::vector<std::thread> th;
     for (size_t g = 0; g < gpus.size(); g++) th.emplace_back(scan_worker, gpus[g], (int)g);

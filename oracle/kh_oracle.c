@@ -583,7 +583,11 @@ void kho_batch_points(const uint8_t base_key[32], const uint8_t stride_be[32], i
 /* ------------------------------------------------------------------------------------------------
  * Targets: bloom + sorted table (readFileAddress keyhunt.cpp:7033.., _sort :4307, searchbinary :3065)
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { uint64_t N; uint8_t *table; obloom *bloom; } otargets;
+typedef struct {
+  uint64_t N; uint8_t *table; obloom *bloom;
+  /* vanity (-m vanity): interval pairs instead of the table, bloom over the first vmin bytes of every A limit */
+  uint64_t vn; uint8_t *va, *vb; int vmin; obloom *vbloom;
+} otargets;
 static int cmp20(const void *a, const void *b) { return memcmp(a, b, 20); }
 void *kho_targets_new(const uint8_t *raw20, uint64_t N) {
   otargets *t = (otargets *)calloc(1, sizeof(otargets));
@@ -595,7 +599,10 @@ void *kho_targets_new(const uint8_t *raw20, uint64_t N) {
   qsort(t->table, N, 20, cmp20);
   return t;
 }
-void kho_targets_free(void *h) { otargets *t = (otargets *)h; if (t) { kho_bloom_free(t->bloom); free(t->table); free(t); } }
+void kho_targets_free(void *h) {
+  otargets *t = (otargets *)h;
+  if (t) { kho_bloom_free(t->bloom); kho_bloom_free(t->vbloom); free(t->table); free(t->va); free(t->vb); free(t); }
+}
 void *kho_targets_bloom(void *h) { return ((otargets *)h)->bloom; }
 const uint8_t *kho_targets_table(void *h, uint64_t *N) { *N = ((otargets *)h)->N; return ((otargets *)h)->table; }
 int kho_searchbinary(void *h, const uint8_t data[20]) { /* keyhunt.cpp:3065-3089, same probe sequence */
@@ -613,6 +620,83 @@ int kho_searchbinary(void *h, const uint8_t data[20]) { /* keyhunt.cpp:3065-3089
     }
   }
   return r;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Vanity targets (-m vanity): addvanity keyhunt.cpp:6739-6860, b58tobin base58/base58.c:39-110,
+ * processOneVanity / readFileVanity :6971-7030, vanityrmdmatch :6677
+ * ---------------------------------------------------------------------------------------------- */
+static const char B58_DIGITS[] = "123456789ABCDEFGHJKLMNPQRSTUVWXYZabcdefghijkmnopqrstuvwxyz";
+/* the reference's decoder: the number fills the WHOLE binsz-byte buffer big-endian (right-aligned); *binsz becomes
+ * (bytes after the leading zero bytes) + (number of leading '1' digits); 0 = invalid digit or overflow */
+int kho_b58tobin(uint8_t *bin, uint64_t *binsz, const char *b58, uint64_t b58sz) {
+  uint64_t n = *binsz, i = 0, zeros = 0;
+  if (!b58sz) b58sz = strlen(b58);
+  memset(bin, 0, n);
+  while (i < b58sz && b58[i] == '1') { zeros++; i++; }
+  for (; i < b58sz; i++) {
+    const char *d = (b58[i] & 0x80) ? NULL : strchr(B58_DIGITS, b58[i]);
+    if (!d || !b58[i]) return 0;
+    uint32_t carry = (uint32_t)(d - B58_DIGITS);
+    for (uint64_t j = n; j-- > 0;) { uint32_t t = (uint32_t)bin[j] * 58u + carry; bin[j] = (uint8_t)t; carry = t >> 8; }
+    if (carry) return 0;
+  }
+  uint64_t lead = 0;
+  while (lead < n && !bin[lead]) lead++;
+  *binsz = n - lead + zeros;
+  return 1;
+}
+/* one side of addvanity: pad the prefix with `fill` until it decodes to more than 25 bytes; every 25-byte decode
+ * contributes bytes 1..20 (the hash160 between version byte and checksum) */
+static int vanity_side(const char *target, char fill, uint8_t *out, int max_r) {
+  char copy[64];
+  uint8_t raw[50];
+  int size = (int)strlen(target), j = 0;
+  memset(copy, 0, sizeof(copy));
+  memcpy(copy, target, (size_t)size);
+  uint64_t len;
+  do {
+    len = 50;
+    kho_b58tobin(raw, &len, copy, (uint64_t)size);           /* a failed decode leaves len = 50 and ends the loop */
+    if (len < 25) copy[size++] = fill;
+    if (len == 25) {
+      uint64_t l2 = 25;
+      kho_b58tobin(raw, &l2, copy, (uint64_t)size);          /* second decode into exactly 25 bytes: version|hash160|checksum */
+      if (j < max_r) memcpy(out + 20 * j, raw + 1, 20);
+      j++;
+      copy[size++] = fill;
+    }
+  } while (len <= 25 && size < 60);
+  return j;
+}
+/* returns r = number of [A,B] pairs for this prefix (0 = not added), *min_bytes lowered like :6833-6836 */
+int kho_addvanity(const char *target, uint8_t *A, uint8_t *B, int max_r, int *min_bytes) {
+  if (strlen(target) >= 30) return 0;
+  uint8_t a[20 * 16], b[20 * 16];
+  int na = vanity_side(target, '1', a, 16), nb = vanity_side(target, 'z', b, 16);
+  if (na < 1 || nb < 1) return 0;
+  int r = na < nb ? na : nb;
+  if (r > 16) r = 16;
+  if (r > max_r) r = max_r;
+  for (int j = 0; j < r; j++) {
+    int same = 0;
+    while (same < 20 && a[20 * j + same] == b[20 * j + same]) same++;
+    if (min_bytes && same < *min_bytes) *min_bytes = same;
+    memcpy(A + 20 * j, a + 20 * j, 20);
+    memcpy(B + 20 * j, b + 20 * j, 20);
+  }
+  return r;
+}
+/* targets handle for a vanity search: n interval pairs (flattened 20-byte limits), bloom of n entries over the first
+ * min_bytes bytes of every A limit (processOneVanity :6971) */
+void *kho_targets_new_vanity(const uint8_t *A, const uint8_t *B, uint64_t n, int min_bytes) {
+  otargets *t = (otargets *)calloc(1, sizeof(otargets));
+  t->vn = n; t->vmin = min_bytes;
+  t->va = (uint8_t *)malloc(n ? n * 20 : 20); t->vb = (uint8_t *)malloc(n ? n * 20 : 20);
+  memcpy(t->va, A, n * 20); memcpy(t->vb, B, n * 20);
+  t->vbloom = (obloom *)kho_bloom_new(n <= 10000 ? 10000 : n);     /* initBloomFilterMapped -> initBloomFilter :7608 */
+  for (uint64_t i = 0; i < n; i++) kho_bloom_add(t->vbloom, A + 20 * i, min_bytes);
+  return t;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -641,6 +725,12 @@ static void job_push_v(scan_job *j, const fe *key, const uint8_t m[20], int kind
   h->index = index;
 }
 static int probe(otargets *t, const uint8_t h[20]) { /* bloom_check then searchbinary, keyhunt.cpp:3621-3624 */
+  if (t->vn) {                                      /* vanityrmdmatch keyhunt.cpp:6677-6703 */
+    if (!kho_bloom_check(t->vbloom, h, t->vmin)) return 0;
+    for (uint64_t i = 0; i < t->vn; i++)
+      if (memcmp(t->va + 20 * i, h, 20) <= 0 && memcmp(t->vb + 20 * i, h, 20) >= 0) return 1;
+    return 0;
+  }
   return kho_bloom_check(t->bloom, h, 20) && kho_searchbinary(t, h);
 }
 

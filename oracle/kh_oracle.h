@@ -70,6 +70,13 @@ void *kho_targets_bloom(void *t);                       /* a kho_bloom handle */
 const uint8_t *kho_targets_table(void *t, uint64_t *N); /* sorted 20-byte records */
 int kho_searchbinary(void *t, const uint8_t data[20]);  /* keyhunt.cpp:3065 */
 
+/* vanity targets (-m vanity): kho_addvanity restates addvanity (keyhunt.cpp:6739) for one base58 prefix and writes its
+ * r interval pairs (20-byte limits, flattened) to A/B, lowering *min_bytes like :6833; kho_targets_new_vanity builds the
+ * handle kho_scan takes (mode KHO_MODE_RMD160, BTC): membership = vanityrmdmatch (:6677) */
+int kho_b58tobin(uint8_t *bin, uint64_t *binsz, const char *b58, uint64_t b58sz);   /* base58/base58.c:39 */
+int kho_addvanity(const char *target, uint8_t *A, uint8_t *B, int max_r, int *min_bytes);
+void *kho_targets_new_vanity(const uint8_t *A, const uint8_t *B, uint64_t n, int min_bytes);
+
 /* scans keys start + i*stride, i in [0, n_points) (n_points multiple of 1024); returns #hits
  * (writes at most max_hits, in ascending index order).  nthreads>1 splits batches over pthreads. */
 int64_t kho_scan(void *targets, int mode, int crypto, int search, const uint8_t start[32],

@@ -26,6 +26,9 @@
 #include "hash/ripemd160.h"
 #define XXH_STATIC_LINKING_ONLY
 #include "xxhash/xxhash.h"
+extern "C" {
+#include "base58/libbase58.h"
+}
 
 static Secp256K1 *g_secp = nullptr;
 
@@ -123,6 +126,13 @@ void khr_eth_addr(const uint8_t xy[64], uint8_t out[20]) {  // keyhunt.cpp:5647-
 }
 
 uint64_t khr_xxh64(const void *buf, uint64_t len, uint64_t seed) { return XXH64(buf, (size_t)len, seed); }
+// base58/base58.c:39 — the decoder addvanity (keyhunt.cpp:6739) leans on, with its whole-buffer / length conventions
+int khr_b58tobin(uint8_t *bin, uint64_t *binsz, const char *b58, uint64_t b58sz) {
+  size_t n = (size_t)*binsz;
+  bool ok = b58tobin(bin, &n, b58, (size_t)b58sz);
+  *binsz = n;
+  return ok ? 1 : 0;
+}
 
 void khr_sha256(const uint8_t *in, uint64_t len, uint8_t out[32]) { sha256((uint8_t *)in, (size_t)len, out); }
 

@@ -168,6 +168,9 @@ class Oracle(_Lib):
         self._sig("bsgs_table", C.POINTER(BpEntry), [C.c_void_p])
         self._sig("bsgs_search", C.c_int, [C.c_void_p, u8p, u8p, u8p, u8p, C.POINTER(C.c_uint64),
                                            C.POINTER(C.c_uint64)])
+        self._sig("b58tobin", C.c_int, [u8p, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64])
+        self._sig("addvanity", C.c_int, [C.c_char_p, u8p, u8p, C.c_int, C.POINTER(C.c_int)])
+        self._sig("targets_new_vanity", C.c_void_p, [u8p, u8p, C.c_uint64, C.c_int])
         self._sig("bsgs_search_ex", C.c_int, [C.c_void_p, u8p, u8p, u8p, C.c_int, u8p, C.POINTER(C.c_uint64),
                                               C.POINTER(C.c_uint64)])
 
@@ -178,6 +181,27 @@ class Oracle(_Lib):
     def targets_new(self, raw20: bytes):
         assert len(raw20) % 20 == 0
         return self._targets_new(raw20, len(raw20) // 20)
+
+    def b58tobin(self, text: bytes, binsz: int):
+        """(ok, reported size, buffer) of the reference-style decoder (base58/base58.c:39)"""
+        buf = C.create_string_buffer(binsz)
+        n = C.c_uint64(binsz)
+        ok = self._b58tobin(buf, C.byref(n), text, len(text))
+        return bool(ok), n.value, buf.raw
+
+    def addvanity(self, prefixes):
+        """addvanity (keyhunt.cpp:6739) over a list of base58 prefixes -> (A limits, B limits, min_bytes, per-prefix r)"""
+        A, B, counts = b"", b"", []
+        mn = C.c_int(999999)
+        for p in prefixes:
+            a, b = C.create_string_buffer(20 * 16), C.create_string_buffer(20 * 16)
+            r = self._addvanity(p.encode() if isinstance(p, str) else p, a, b, 16, C.byref(mn))
+            counts.append(r)
+            A += a.raw[:20 * r]; B += b.raw[:20 * r]
+        return A, B, mn.value, counts
+
+    def targets_new_vanity(self, A: bytes, B: bytes, min_bytes: int):
+        return self._targets_new_vanity(A, B, len(A) // 20, min_bytes)
 
     def targets_free(self, t):
         self._targets_free(t)
@@ -240,8 +264,15 @@ class RefHarness(_Lib):
     def __init__(self):
         super().__init__(REF_SO, "khr_")
         self._sig("hash160_scalar", None, [C.c_int, C.c_char_p, C.c_char_p])
+        self._sig("b58tobin", C.c_int, [C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64])
         self._sig("sizeof_bloom", C.c_int, [])
         self.lib.khr_init()
+
+    def b58tobin(self, text: bytes, binsz: int):
+        buf = C.create_string_buffer(binsz)
+        n = C.c_uint64(binsz)
+        ok = self._b58tobin(buf, C.byref(n), text, len(text))
+        return bool(ok), n.value, buf.raw
 
     def hash160_scalar(self, compressed, x, y):
         o = C.create_string_buffer(20); self._hash160_scalar(1 if compressed else 0, be32(x) + be32(y), o); return o.raw

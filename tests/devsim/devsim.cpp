@@ -55,6 +55,11 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
   scratch.resize((size_t)1024 * ws.T);
 }
 
+// -m vanity for the next ds_scan calls: van = 2048-word prefix bitmap + n x (A[5], B[5]) big-endian words (ScanTargets::van); n = 0 switches it off
+static const uint32_t *g_van = nullptr;
+static uint32_t g_van_n = 0;
+void ds_set_vanity(const uint32_t *van, uint32_t n) { g_van = van; g_van_n = n; }
+
 // kind: KH_SCAN_*; table20: N sorted 20-byte records; bloom image as bytes
 int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint8_t *bloom_bytes, uint64_t bloom_bits,
                 uint32_t bloom_hashes, const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T,
@@ -81,6 +86,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
   tg.bloom.bits = bloom_bits; tg.bloom.magic = (~0ULL) / bloom_bits; tg.bloom.stride = 0; tg.bloom.hashes = bloom_hashes;
   tg.table = table.data(); tg.n = n_targets;
   tg.sink.hits = raw.data(); tg.sink.count = &count; tg.sink.cap = max_hits;
+  tg.van = g_van; tg.van_n = g_van_n; tg.van_pad = 0;
 
   WalkParams wp;
   wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
@@ -88,7 +94,13 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;
     for (uint64_t t = 0; t < T; t++) {
-      switch (kind + (endo ? 8 : 0)) {
+      switch (kind + (endo ? 8 : 0) + (g_van_n ? 16 : 0)) {
+        case 16 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 16 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 16 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         case KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }

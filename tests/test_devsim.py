@@ -163,3 +163,44 @@ def test_scan_emit_logic_endomorphism(ds, oracle, name):
     got = sorted((hits[i].index, hits[i].kind, hits[i].variant, bytes(hits[i].matched)) for i in range(cnt))
     assert got == sorted((h["index"], h["kind"], h["variant"], h["matched"]) for h in want)
     assert cnt >= 10
+
+
+def _vanity_words(A, B):
+    """what kh_set_vanity uploads (kh_scan.cu): 16-bit prefix bitmap + limits as big-endian words"""
+    n = len(A) // 20
+    van = [0] * (2048 + 10 * n)
+    for i in range(n):
+        a, b = A[20 * i:20 * i + 20], B[20 * i:20 * i + 20]
+        for k in range(5):
+            van[2048 + 10 * i + k] = int.from_bytes(a[4 * k:4 * k + 4], "big")
+            van[2048 + 10 * i + 5 + k] = int.from_bytes(b[4 * k:4 * k + 4], "big")
+        if a <= b:
+            for p in range(int.from_bytes(a[:2], "big"), int.from_bytes(b[:2], "big") + 1):
+                van[p >> 5] |= 1 << (p & 31)
+    return (C.c_uint32 * len(van))(*van), n
+
+
+@pytest.mark.parametrize("name", ["comp", "uncomp", "both"])
+def test_scan_emit_logic_vanity(ds, oracle, name):
+    """-m vanity: the device interval test (vanity_match) on the walk's digests == the oracle's vanityrmdmatch, for
+    the reference's own prefix decoding (addvanity) of short prefixes that hit within a few thousand keys"""
+    kind, mode, crypto, search = KINDS[name]
+    A, B, mn, counts = oracle.addvanity(["1A", "1Bi", "1zz", "12"])
+    assert min(counts) >= 1
+    t = oracle.targets_new_vanity(A, B, mn)
+    start, stride, nb, T = 0x5000000000000123, 1, 8, 4
+    want = oracle.scan(t, mode, crypto, search, start, stride, nb * 1024, nthreads=2, max_hits=8192)
+    oracle.targets_free(t)
+    van, n = _vanity_words(A, B)
+    ds.ds_set_vanity.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
+    ds.ds_set_vanity.restype = None
+    ds.ds_set_vanity(van, n)
+    try:
+        hits = (DsHit * 8192)()
+        dummy = b"\0" * 20
+        cnt = ds.ds_scan(kind, dummy, 1, b"\0" * 64, 512, 1, be32(start), be32(stride), nb, T, 2, hits, 8192, 0)
+    finally:
+        ds.ds_set_vanity(None, 0)
+    got = sorted((hits[i].index, hits[i].kind, bytes(hits[i].matched)) for i in range(cnt))
+    assert got == sorted((h["index"], h["kind"], h["matched"]) for h in want)
+    assert cnt >= 100
