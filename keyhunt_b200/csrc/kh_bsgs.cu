@@ -403,14 +403,16 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
   if (rc) return rc;
 
   // candidate queue + result
+  // candidate queue, counters ([0] candidate count, [1] found flag) and the found key live in the context: a server
+  // answers thousands of requests with the same three buffers
   const uint32_t cap = 1u << 16;
-  GiantCand *d_cands = nullptr;
-  uint32_t *d_cnt = nullptr;       // [0] candidate count, [1] found flag
-  u256 *d_key = nullptr;
-  KH_CUDA(c, cudaMalloc(&d_cands, cap * sizeof(GiantCand)));
-  KH_CUDA(c, cudaMalloc(&d_cnt, 4 * sizeof(uint32_t)));
-  KH_CUDA(c, cudaMalloc(&d_key, sizeof(u256)));
-  cudaMemsetAsync(d_cnt, 0, 4 * sizeof(uint32_t), c->stream);
+  if (!c->d_giant_cands) KH_CUDA(c, cudaMalloc(&c->d_giant_cands, cap * sizeof(GiantCand)));
+  if (!c->d_giant_cnt) KH_CUDA(c, cudaMalloc(&c->d_giant_cnt, 4 * sizeof(uint32_t)));
+  if (!c->d_giant_key) KH_CUDA(c, cudaMalloc(&c->d_giant_key, sizeof(u256)));
+  GiantCand *d_cands = static_cast<GiantCand *>(c->d_giant_cands);
+  uint32_t *d_cnt = c->d_giant_cnt;
+  u256 *d_key = static_cast<u256 *>(c->d_giant_key);
+  KH_CUDA(c, cudaMemsetAsync(d_cnt, 0, 4 * sizeof(uint32_t), c->stream));
 
   BsgsTables bt;
   fill_tables(c, bt);
@@ -463,7 +465,8 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
       if (e != cudaSuccess) { result = kh_fail(c, KH_ENODEV, "refine kernel: %s", cudaGetErrorString(e)); break; }
       if (f) {
         u256 key;
-        cudaMemcpy(&key, d_key, sizeof(key), cudaMemcpyDeviceToHost);
+        cudaMemcpyAsync(&key, d_key, sizeof(key), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
         u256_to_be(found_key_be, key);
         *found = 1;
       }
@@ -471,7 +474,6 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
   }
   c->stats.points += steps_done;
   c->stats.walker_threads = T;
-  cudaFree(d_cands); cudaFree(d_cnt); cudaFree(d_key);
   if (result == KH_OK && c->overflowed) { c->overflowed = false; return kh_fail(c, KH_EOVERFLOW, "tier-1 candidate queue overflowed"); }
   return result;
 }

@@ -61,6 +61,9 @@ struct kh_ctx {
   uint64_t tier_stride[3] = {0, 0, 0};
   kh::BpEntry *d_bptable = nullptr;
   uint32_t *d_aux_tab = nullptr;   // AMP2/AMP3 + helper points for refinement
+  void *d_giant_cands = nullptr;   // tier-1 positives of one launch (kh::GiantCand[65536])
+  uint32_t *d_giant_cnt = nullptr; // [0] candidate count, [1] found flag
+  void *d_giant_key = nullptr;     // found key (kh::u256)
 
   kh_stats stats{};
 };

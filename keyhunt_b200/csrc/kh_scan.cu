@@ -187,7 +187,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
