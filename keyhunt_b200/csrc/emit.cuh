@@ -59,8 +59,18 @@ struct ScanTargets {
   // then van_n x (A[5], B[5]) as big-endian-packed words.
   const uint32_t *van;
   uint32_t van_n;
-  uint32_t van_pad;
+  // exact pre-filter in front of the bloom: 2^pre_k bits (16 <= pre_k <= 32) indexed by the first pre_k bits of the 20-byte
+  // record, set for every target (no false negatives, so bloom AND table give the same hits with or without it).  Sized
+  // so that a warp rarely holds any passing lane (<= 0.4 % fill up to 2^24 targets): then the two XXH64 + the bloom probes
+  // (~170 instructions per record, more for the warp-divergent tail of a half-full filter) are skipped for the whole
+  // warp.  Always present: "prefilter" = 0 uploads an all-ones bitmap.
+  uint32_t pre_k;
+  const uint32_t *pre;
 };
+KH_HD bool prefilter_pass(const ScanTargets &tg, uint32_t first_word_be) {
+  const uint32_t idx = first_word_be >> (32 - tg.pre_k);
+  return (kh_ld_u32(tg.pre + (idx >> 5)) >> (idx & 31)) & 1u;
+}
 
 // vanityrmdmatch (keyhunt.cpp:6677-6703): the reference pre-filters with a bloom over the first
 // vanity_rmd_minimun_bytes_check_length bytes of every lower limit; every value inside an interval shares those
@@ -99,6 +109,7 @@ struct ScanEmit {
       if (vanity_match(tg.van, tg.van_n, h)) sink_push(tg.sink, batch, idx, kind, h, variant);
       return;
     }
+    if (!prefilter_pass(tg, bswap32(h[0]))) return;
     if (bloom_check20(tg.bloom, h)) {                  // keyhunt.cpp:3621
       if (table_contains(tg.table, tg.n, h))           // keyhunt.cpp:3623
         sink_push(tg.sink, batch, idx, kind, h, variant);
@@ -153,9 +164,10 @@ struct ScanEmit {
     uint32_t ha[5], hb[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) { ha[i] = bswap32(xa.v[7 - i]); hb[i] = bswap32(xb.v[7 - i]); }
+    bool okA = prefilter_pass(tg, xa.v[7]), okB = prefilter_pass(tg, xb.v[7]);
+    if (!(okA || okB)) return;
     const uint64_t aA = xxh64_20(ha, KH_BLOOM_SEED), aB = xxh64_20(hb, KH_BLOOM_SEED);
     const uint64_t bA = xxh64_20(ha, aA), bB = xxh64_20(hb, aB);
-    bool okA = true, okB = true;
     bloom_test_pair(tg.bloom, 0, aA, bA, 0, aB, bB, okA, okB);
     if (okA && table_contains(tg.table, tg.n, ha)) sink_push(tg.sink, batch, ia, KH_KIND_XPOINT, ha);
     if (okB && table_contains(tg.table, tg.n, hb)) sink_push(tg.sink, batch, ib, KH_KIND_XPOINT, hb);

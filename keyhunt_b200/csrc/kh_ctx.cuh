@@ -26,6 +26,7 @@ struct kh_ctx {
   int steps_per_launch = 16;
   uint32_t hit_capacity = 1u << 16;
   int endomorphism = 0;            // -e: test beta*x and beta^2*x of every point too
+  int prefilter = 1;               // exact prefix bitmap in front of the bloom for target sets of <= 65,536 records
   int bsgs_base_check = 0;         // server variant of the BSGS search (bsgsd.cpp:2544)
 
   // walk state
@@ -43,6 +44,8 @@ struct kh_ctx {
   uint32_t *d_table = nullptr;     // N x 5 BE words
   uint64_t n_targets = 0;
   std::vector<uint8_t> h_table20;  // sorted records (host copy for kh_get_table)
+  uint32_t *d_pre = nullptr;       // exact prefix bitmap in front of the bloom (ScanTargets::pre), 2^pre_k bits
+  uint32_t pre_k = 0;
   uint32_t *d_vanity = nullptr;    // -m vanity: prefix bitmap + interval limits (ScanTargets::van)
   uint32_t n_vanity = 0;
 

@@ -187,7 +187,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -207,6 +207,8 @@ int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
     c->steps_per_launch = (int)value;
   } else if (!strcmp(name, "endomorphism")) {      // -e (FLAGENDOMORPHISM, keyhunt.cpp:924)
     c->endomorphism = value ? 1 : 0;
+  } else if (!strcmp(name, "prefilter")) {         // exact prefix bitmap in front of the bloom (takes effect at the next kh_set_targets)
+    c->prefilter = value ? 1 : 0;
   } else if (!strcmp(name, "bsgs_base_check")) {   // the reference SERVER's search loop (bsgsd.cpp:2544)
     c->bsgs_base_check = value ? 1 : 0;
   } else if (!strcmp(name, "hit_capacity")) {
@@ -289,6 +291,18 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
     kh_bloom_build<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(bl, c->d_table, n);
     c->stats.aux_ms += kh_time_end(c);
     c->stats.other_launches += 1;
+  }
+  // prefix bitmap (ScanTargets::pre): >= 256 bits per target (fill <= 0.4 %) between 2^16 and 2^32 bits (8 KB .. 512 MB)
+  {
+    if (c->d_pre) { cudaFree(c->d_pre); c->d_pre = nullptr; }
+    uint32_t k = 16;
+    if (c->prefilter) while (k < 32 && (1ull << k) < 256ull * n) k++;
+    std::vector<uint32_t> bm((size_t)1 << (k - 5), c->prefilter ? 0u : 0xFFFFFFFFu);
+    for (uint64_t i = 0; i < n; i++) { const uint32_t idx = packed[5 * i] >> (32 - k); bm[idx >> 5] |= 1u << (idx & 31); }
+    KH_CUDA(c, cudaMalloc(&c->d_pre, bm.size() * sizeof(uint32_t)));
+    KH_CUDA(c, cudaMemcpyAsync(c->d_pre, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    KH_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->pre_k = k;
   }
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
   KH_CUDA(c, cudaGetLastError());
@@ -407,7 +421,8 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
 
   ScanTargets tg;
   const bool vanity = (c->mode == KH_MODE_VANITY);
-  tg.van = vanity ? c->d_vanity : nullptr; tg.van_n = vanity ? c->n_vanity : 0u; tg.van_pad = 0;
+  tg.van = vanity ? c->d_vanity : nullptr; tg.van_n = vanity ? c->n_vanity : 0u;
+  tg.pre = c->d_pre; tg.pre_k = c->pre_k;
   tg.bloom.bf = c->d_bloom; tg.bloom.bits = c->bloom_desc.bits; tg.bloom.magic = vanity ? 0ull : (~0ULL) / c->bloom_desc.bits;
   tg.bloom.stride = 0; tg.bloom.hashes = c->bloom_desc.hashes; tg.bloom.pad = 0;
   tg.table = c->d_table; tg.n = c->n_targets;

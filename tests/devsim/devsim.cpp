@@ -86,7 +86,16 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
   tg.bloom.bits = bloom_bits; tg.bloom.magic = (~0ULL) / bloom_bits; tg.bloom.stride = 0; tg.bloom.hashes = bloom_hashes;
   tg.table = table.data(); tg.n = n_targets;
   tg.sink.hits = raw.data(); tg.sink.count = &count; tg.sink.cap = max_hits;
-  tg.van = g_van; tg.van_n = g_van_n; tg.van_pad = 0;
+  tg.van = g_van; tg.van_n = g_van_n; tg.pre = nullptr; tg.pre_k = 0;
+  // the prefix bitmap exactly as kh_set_targets sizes and fills it (kh_scan.cu)
+  std::vector<uint32_t> bm;
+  {
+    uint32_t k = 16;
+    while (k < 32 && (1ull << k) < 256ull * n_targets) k++;
+    bm.assign((size_t)1 << (k - 5), 0u);
+    for (uint64_t i = 0; i < n_targets; i++) { const uint32_t idx = table[5 * i] >> (32 - k); bm[idx >> 5] |= 1u << (idx & 31); }
+    tg.pre = bm.data(); tg.pre_k = k;
+  }
 
   WalkParams wp;
   wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
