@@ -45,7 +45,7 @@ WORKLOADS = {
                start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
                mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162, disp=1,
-               alu_ops=7500),   # ncu: ALU-pipe thread instructions per point of kh_scan_kernel<BOTH> (profiles/r01_final_both_ncu_sections.txt)
+               alu_ops=6830),   # ncu (profiles/r01_prefilter_both_ncu_sections.txt): 42.46 G warp instructions per 2^27 points, ALU share = (86.5 % x 0.5/clk) / 64.1 % issue = 67.5 % -> 6,830 ALU thread-ops per point
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
                mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, disp=1),
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
