@@ -138,18 +138,20 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": "C4 bsgs -k %d, n=2^44 (m=2^%d), 1 public key, range [2^64, 2^65), step = 2^15 windows = 2^28 giant steps"
                                % (args.k, d.m.bit_length() - 1), "gpu": info["name"],
-                   "l2_note": "tier-1 bloom (%.1f GB) is far larger than L2; every probe is a random HBM sector" % build["tier1_GB"]},
+                   "l2_note": "tier-1 bloom (%.1f GB) and its prefix bitmap (64 GB) are far larger than L2; every probe is a random HBM sector" % build["tier1_GB"]},
         "clocks": clk, "build": build,
         "giant_steps_per_s": gs, "wall_ms_per_step": wall * 1e3 / args.steps,
         "planted": {"found": got == key, "time_to_find_s": t_find},
         "e2e": {"value": steps_total * 2 * d.m / wall / 1e15, "unit": "Pkeys/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 48, "steps": args.steps},
         "gpu_launches": st["walk_launches"] + st["other_launches"], "tier1_positives": st["tier1_positives"],
         "roofline": {"bound": "hbm", "achieved": gs * 64 / 1e9, "peak": hbm, "unit": "GB/s", "frac": gs * 64 / 1e9 / hbm,
-                     "traffic": 243.0 * (st["points"] / max(1, st["walk_launches"])),
+                     "traffic": 161.0 * (st["points"] / max(1, st["walk_launches"])),
                      "kernel": "kh_giant_kernel", "bytes_per_giant_step": 64,
-                     "note": "algorithmic 64 B/step (2 random 32-B sectors, SURVEY §8d); ncu measures 243 B of DRAM reads per step "
-                             "(every 1-byte probe costs a 64-B DRAM atom + scratch), i.e. 2.5 TB/s = 39 % of the measured copy bandwidth "
-                             "on a purely random pattern (profiles/r01_giant_ncu_metrics.csv)",
+                     "note": "algorithmic 64 B/step (SURVEY §8d: 2 random 32-B sectors; here 16 B + 16 B of prefix-product scratch and one "
+                             "32-B sector of the baby-point prefix bitmap that answers for the tier-1 bloom); ncu measures 145 B read + "
+                             "16 B written per step: the single random probe into the 64 GB bitmap costs ~4 sectors (a 64-B DRAM atom plus "
+                             "page-table reads), DRAM 38.7 % of peak on a purely random pattern, FMA-heavy pipe 69 % busy "
+                             "(profiles/r01_giant_prefilter_ncu_metrics.csv; without the bitmap: 243 B per step, r01_giant_ncu_metrics.csv)",
                      "int_ops_per_step": 920, "int_tiops": gs * 920 / 1e12},
         "cpu_baseline": cpu,
     }

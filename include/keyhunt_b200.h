@@ -44,6 +44,8 @@ const char *kh_last_error(kh_ctx *ctx);
  * "prefilter" (default 1; 0 = no prefix bitmap in front of the bloom: kh_set_targets normally also builds an exact bitmap over
  *  the first 16..32 bits of every target record, which lets whole warps skip the two XXH64 + bloom probes; hits are identical
  *  either way, the bloom image and table returned by kh_get_bloom / kh_get_table are unaffected),
+ * "bsgs_prefilter" (default 1: kh_bsgs_build also fills an exact bitmap over the first bits of every baby point's X, up to
+ *  3/4 of the free HBM, which answers most tier-1 probes with one memory access; found keys are identical),
  * "bsgs_base_check" (1 = kh_bsgs_search behaves like the reference SERVER's loop, which also reports a key equal to
  *  the base key of a 2N window, bsgsd.cpp:2544; 0 = keyhunt.cpp's thread_process_bsgs, the default) */
 int kh_set_option(kh_ctx *ctx, const char *name, int64_t value);

@@ -208,7 +208,18 @@ struct BsgsTables {
   BloomDev tier[3];       // bloom_bP, bloom_bPx2nd, bloom_bPx3rd: 256 shards each, shard = X[0]
   BpEntry *table;         // m3 entries
   uint64_t m, m2, m3;
+  // exact prefix bitmap over the baby points' X (same idea as ScanTargets::pre): 2^pre_k bits indexed by the first pre_k
+  // bits of X, set for every baby point; a giant step whose bit is clear cannot be a baby point, so its tier-1 probes
+  // (~4 random 64-byte HBM atoms) are replaced by this one.  pre_k = 0: off.
+  uint32_t *pre;
+  uint32_t pre_k;
+  uint32_t pad;
 };
+KH_HD uint64_t bsgs_pre_index(const fe &x, uint32_t k) { return (((uint64_t)x.v[7] << 32) | x.v[6]) >> (64 - k); }
+KH_HD bool bsgs_pre_test(const uint32_t *pre, uint32_t k, const fe &x) {
+  const uint64_t idx = bsgs_pre_index(x, k);
+  return (kh_ld_u32(pre + (idx >> 5)) >> (uint32_t)(idx & 31)) & 1u;
+}
 
 // baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
 struct BabyEmit {
@@ -243,6 +254,14 @@ struct BabyEmit {
     }
     if (p < bt.m2) bloom_set(bt.tier[1], shard, a, b);
     bloom_set(bt.tier[0], shard, a, b);
+    if (bt.pre_k) {
+      const uint64_t idx = bsgs_pre_index(x, bt.pre_k);
+#ifdef __CUDA_ARCH__
+      atomicOr(bt.pre + (idx >> 5), 1u << (uint32_t)(idx & 31));
+#else
+      bt.pre[idx >> 5] |= 1u << (uint32_t)(idx & 31);
+#endif
+    }
   }
 };
 
@@ -257,8 +276,9 @@ struct GiantParams {
   GiantCand *cands;
   uint32_t *count;
   uint32_t cap;
-  uint32_t pad;
+  uint32_t pre_k;          // BsgsTables::pre / pre_k (0 = off)
   uint64_t n_steps;        // giant steps >= n_steps are outside the reference's walk and are skipped
+  const uint32_t *pre;
 };
 #ifndef KH_GIANT_OUTLINE
 #define KH_GIANT_OUTLINE 0
@@ -273,12 +293,17 @@ struct GiantEmit {
   }
   // two giant steps at once: 2 x 2 XXH64 chains interleaved, tier-1 probes of both in flight together
   KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
+    bool okA = (batch * KH_GRP + ia) < gp.n_steps, okB = (batch * KH_GRP + ib) < gp.n_steps;
+    if (gp.pre_k) {
+      okA = okA && bsgs_pre_test(gp.pre, gp.pre_k, xa);
+      okB = okB && bsgs_pre_test(gp.pre, gp.pre_k, xb);
+      if (!(okA || okB)) return;
+    }
     uint32_t wa[8], wb[8];
     fe_to_le_words(wa, xa);
     fe_to_le_words(wb, xb);
     const uint64_t aA = xxh64_32(wa, KH_BLOOM_SEED), aB = xxh64_32(wb, KH_BLOOM_SEED);
     const uint64_t bA = xxh64_32(wa, aA), bB = xxh64_32(wb, aB);
-    bool okA = (batch * KH_GRP + ia) < gp.n_steps, okB = (batch * KH_GRP + ib) < gp.n_steps;
     bloom_test_pair(gp.tier1, xa.v[7] >> 24, aA, bA, xb.v[7] >> 24, aB, bB, okA, okB);
     if (okA) push(batch, ia);
     if (okB) push(batch, ib);
@@ -287,6 +312,7 @@ struct GiantEmit {
   KH_HDM explicit GiantEmit(const GiantParams &g) : gp(g) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
     if (batch * KH_GRP + idx >= gp.n_steps) return;
+    if (gp.pre_k && !bsgs_pre_test(gp.pre, gp.pre_k, x)) return;
     uint32_t w[8];
     fe_to_le_words(w, x);
     const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);

@@ -73,6 +73,14 @@ __global__ void kh_bitonic_step(BpEntry *tab, uint64_t n2, uint64_t j, uint64_t 
   if (a_gt_b == ascending) { tab[i] = b; tab[ixj] = a; }
 }
 
+// sets *flag when two byte ranges differ (kh_bsgs_import)
+__global__ void kh_diff_kernel(const uint8_t *a, const uint8_t *b, uint64_t n, uint32_t *flag) {
+  const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  bool diff = false;
+  for (uint64_t i = i0; i < n && i < i0 + 16; i++) diff |= (a[i] != b[i]);
+  if (diff) atomicOr(flag, 1u);
+}
+
 // ---- AMP tables: entry i (<32) = -(2i+1)*m2*G, entry 32+i = -(2i+1)*m3*G ------------------------------
 __global__ void __launch_bounds__(64) kh_amp_kernel(uint32_t *aux, uint64_t m2, uint64_t m3) {
   const uint32_t i = threadIdx.x;
@@ -213,6 +221,8 @@ static int ilog2_exact(uint64_t n) {
 }
 static void free_bsgs(kh_ctx *c) {
   for (int t = 0; t < 3; t++) { if (c->d_tier[t]) cudaFree(c->d_tier[t]); c->d_tier[t] = nullptr; }
+  if (c->d_bsgs_pre) cudaFree(c->d_bsgs_pre);
+  c->d_bsgs_pre = nullptr; c->bsgs_pre_k = 0;
   if (c->d_bptable) cudaFree(c->d_bptable);
   if (c->d_aux_tab) cudaFree(c->d_aux_tab);
   c->d_bptable = nullptr; c->d_aux_tab = nullptr;
@@ -229,6 +239,7 @@ static void fill_tables(kh_ctx *c, BsgsTables &bt) {
   }
   bt.table = c->d_bptable;
   bt.m = c->bsgs.m; bt.m2 = c->bsgs.m2; bt.m3 = c->bsgs.m3;
+  bt.pre = c->d_bsgs_pre; bt.pre_k = c->bsgs_pre_k; bt.pad = 0;
 }
 
 extern "C" {
@@ -277,6 +288,23 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
   ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
   rc = kh_run_setup(c, ws);
   if (rc) return rc;
+  // prefix bitmap over the baby points: 256 bits per point (0.4 % fill) when HBM allows, never more than 3/4 of what is
+  // free now (the walk buffers are already allocated), never less than 8 bits per point (then it is not worth a probe)
+  if (c->bsgs_prefilter) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint32_t k = 20;
+    while (k < 48 && (1ull << k) < 256ull * d.m) k++;
+    while (k > 20 && (1ull << (k - 3)) > (uint64_t)free_b / 4 * 3) k--;
+    if (const char *e = getenv("KH_BSGS_PRE_LOG2")) { const uint32_t cap = (uint32_t)atoi(e); if (cap >= 20 && cap < k) k = cap; }   // experiments
+    if ((1ull << k) >= 8ull * d.m && cudaMalloc(&c->d_bsgs_pre, (size_t)1 << (k - 3)) == cudaSuccess) {
+      KH_CUDA(c, cudaMemsetAsync(c->d_bsgs_pre, 0, (size_t)1 << (k - 3), c->stream));
+      c->bsgs_pre_k = k;
+    } else {
+      cudaGetLastError();
+      c->d_bsgs_pre = nullptr;
+    }
+  }
   BsgsTables bt;
   fill_tables(c, bt);
   WalkParams wp;
@@ -348,6 +376,23 @@ int kh_bsgs_import(kh_ctx *c, int tier, int shard, const void *src, uint64_t n) 
   int rc = bsgs_region(c, tier, shard, &p, &len);
   if (rc) return rc;
   if (n != len) return kh_fail(c, KH_EINVAL, "length mismatch (%llu != %llu)", (unsigned long long)n, (unsigned long long)len);
+  if (tier == 1 && c->bsgs_pre_k) {
+    // the prefix bitmap describes the baby points kh_bsgs_build walked: it stays valid only while tier 1 holds exactly
+    // what was built (the normal case: files written by a build with the same n / k); anything else switches it off
+    uint8_t *tmp = nullptr;
+    uint32_t *d_flag = nullptr, h_flag = 0;
+    KH_CUDA(c, cudaMalloc(&tmp, len));
+    KH_CUDA(c, cudaMalloc(&d_flag, sizeof(uint32_t)));
+    cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), c->stream);
+    cudaMemcpyAsync(tmp, src, len, cudaMemcpyHostToDevice, c->stream);
+    kh_diff_kernel<<<(unsigned)((len + 256 * 16 - 1) / (256 * 16)), 256, 0, c->stream>>>(p, tmp, len, d_flag);
+    cudaMemcpyAsync(&h_flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (h_flag) { cudaMemcpyAsync(p, tmp, len, cudaMemcpyDeviceToDevice, c->stream); cudaStreamSynchronize(c->stream); c->bsgs_pre_k = 0; }
+    cudaFree(tmp); cudaFree(d_flag);
+    KH_CUDA(c, cudaGetLastError());
+    return KH_OK;
+  }
   KH_CUDA(c, cudaMemcpyAsync(p, src, len, cudaMemcpyHostToDevice, c->stream));
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
   return KH_OK;
@@ -417,7 +462,8 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
   BsgsTables bt;
   fill_tables(c, bt);
   GiantParams gp;
-  gp.tier1 = bt.tier[0]; gp.cands = d_cands; gp.count = d_cnt; gp.cap = cap; gp.pad = 0; gp.n_steps = n_steps;
+  gp.tier1 = bt.tier[0]; gp.cands = d_cands; gp.count = d_cnt; gp.cap = cap; gp.n_steps = n_steps;
+  gp.pre = c->d_bsgs_pre; gp.pre_k = c->bsgs_pre_k;
   RefineParams rp;
   rp.bt = bt; rp.aux = c->d_aux_tab; rp.cands = d_cands; rp.n_cands = 0; rp.base_check = (uint32_t)c->bsgs_base_check; rp.steps_per_window = d.aux;
   rp.q = ws.q; rp.start = start; rp.found = d_cnt + 1; rp.found_key = d_key;

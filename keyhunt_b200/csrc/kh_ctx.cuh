@@ -27,6 +27,7 @@ struct kh_ctx {
   uint32_t hit_capacity = 1u << 16;
   int endomorphism = 0;            // -e: test beta*x and beta^2*x of every point too
   int prefilter = 1;               // exact prefix bitmap in front of the bloom for target sets of <= 65,536 records
+  int bsgs_prefilter = 1;          // build the baby-point prefix bitmap when HBM allows (kh_bsgs_build)
   int bsgs_base_check = 0;         // server variant of the BSGS search (bsgsd.cpp:2544)
 
   // walk state
@@ -64,6 +65,8 @@ struct kh_ctx {
   uint64_t tier_stride[3] = {0, 0, 0};
   kh::BpEntry *d_bptable = nullptr;
   uint32_t *d_aux_tab = nullptr;   // AMP2/AMP3 + helper points for refinement
+  uint32_t *d_bsgs_pre = nullptr;  // exact prefix bitmap over the baby points' X (BsgsTables::pre), 2^bsgs_pre_k bits
+  uint32_t bsgs_pre_k = 0;
   void *d_giant_cands = nullptr;   // tier-1 positives of one launch (kh::GiantCand[65536])
   uint32_t *d_giant_cnt = nullptr; // [0] candidate count, [1] found flag
   void *d_giant_key = nullptr;     // found key (kh::u256)

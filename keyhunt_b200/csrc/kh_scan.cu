@@ -209,6 +209,8 @@ int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
     c->endomorphism = value ? 1 : 0;
   } else if (!strcmp(name, "prefilter")) {         // exact prefix bitmap in front of the bloom (takes effect at the next kh_set_targets)
     c->prefilter = value ? 1 : 0;
+  } else if (!strcmp(name, "bsgs_prefilter")) {    // baby-point prefix bitmap in front of the tier-1 bloom (next kh_bsgs_build)
+    c->bsgs_prefilter = value ? 1 : 0;
   } else if (!strcmp(name, "bsgs_base_check")) {   // the reference SERVER's search loop (bsgsd.cpp:2544)
     c->bsgs_base_check = value ? 1 : 0;
   } else if (!strcmp(name, "hit_capacity")) {

@@ -9,6 +9,8 @@ k = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 o = Oracle()
 kh = K.KeyHunt(0)
 import os
+if os.environ.get('KH_BSGS_PREFILTER'):
+    kh.set_option('bsgs_prefilter', int(os.environ['KH_BSGS_PREFILTER']))
 if os.environ.get('KH_TPS'):
     kh.set_option('threads_per_sm', int(os.environ['KH_TPS']))
 t0 = time.time()
