@@ -202,3 +202,41 @@ def test_c2_quarter_size_planted_only(kh):
     hits = kh.poll_hits()
     assert sorted(h.key for h in hits) == [start + i for i in idx]
     assert {h.kind for h in hits} == {K.HIT_COMP02, K.HIT_COMP03, K.HIT_UNCOMP}
+
+
+@pytest.mark.parametrize("n_decoys", [0, 1000, 300000])
+def test_prefilter_never_changes_the_hits(kh, oracle, n_decoys):
+    """the exact prefix bitmap in front of the bloom (option "prefilter", on by default; bitmap 2^16 .. 2^27 bits here): same hits
+    with it, without it (all-ones bitmap), and from the oracle, for every scan kind incl. targets that share their first bytes"""
+    import numpy as np
+    rnd = random.Random(77 + n_decoys)
+    start, stride, n_points = 0x7000000000000123, 1, 1 << 15
+    decoys = np.random.default_rng(n_decoys).integers(0, 256, size=n_decoys * 20, dtype=np.uint8).tobytes()
+    for name, mode, crypto, search, omode, ocrypto in (("both", K.MODE_RMD160, K.CRYPTO_BTC, SEARCH_BOTH, O_RMD, O_BTC),
+                                                       ("xpoint", K.MODE_XPOINT, K.CRYPTO_BTC, SEARCH_COMPRESS, O_XP, O_BTC),
+                                                       ("eth", K.MODE_ADDRESS, K.CRYPTO_ETH, SEARCH_COMPRESS, O_ADDR, O_ETH)):
+        recs = []
+        for i in sorted({0, 1, 1023, 1024, n_points - 1} | {rnd.randrange(n_points) for _ in range(40)}):
+            x, y = oracle.pubkey(start + i * stride)
+            if name == "xpoint":
+                recs.append(be32(x)[:20])
+            elif name == "eth":
+                recs.append(oracle.eth_addr(x, y))
+            else:
+                recs.append(oracle.hash160_uncomp(x, y) if i % 2 else oracle.hash160_comp(2 + (y & 1), x))
+        near = [r[:3] + rnd.randbytes(17) for r in recs[:10]]          # same first 24 bits as a real target, not targets
+        blob = b"".join(recs + near) + decoys
+        t = oracle.targets_new(blob)
+        want = _ohits_set(oracle.scan(t, omode, ocrypto, search, start, stride, n_points))
+        oracle.targets_free(t)
+        got = {}
+        try:
+            for pf in (1, 0):
+                kh.set_option("prefilter", pf)
+                kh.set_targets(mode, blob, crypto=crypto, search=search)
+                kh.scan(start, n_points, stride)
+                got[pf] = _hits_set(kh.poll_hits())
+        finally:
+            kh.set_option("prefilter", 1)
+        assert got[1] == got[0] == want, name
+        assert len(want) >= 40
