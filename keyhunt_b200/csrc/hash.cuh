@@ -129,12 +129,19 @@ KH_HD uint32_t sha_k(int i) {
 #ifndef KH_SHA_ROLLED
 #define KH_SHA_ROLLED 1
 #endif
-KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+// shape (KH_SHA_SPECIAL): 0 = any block, 1 = the 33-byte compressed-key block, 2 = the second block of the 65-byte key; the
+// first schedule expansion then drops the zero words and folds sigma(constant) (gen_rounds.py emit_special)
+#ifndef KH_SHA_SPECIAL
+#define KH_SHA_SPECIAL 1
+#endif
+KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16], int shape = 0) {
   uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #if KH_SHA_ROLLED
 #pragma unroll 1
   for (int kb = 0; kb < 64; kb += 16) {
-    if (kb) { KH_SHA256_EXPAND16(w); }
+    if (KH_SHA_SPECIAL && kb == 16 && shape == 1) { KH_SHA256_EXPAND16_COMP33(w); }
+    else if (KH_SHA_SPECIAL && kb == 16 && shape == 2) { KH_SHA256_EXPAND16_UNC2(w); }
+    else if (kb) { KH_SHA256_EXPAND16(w); }
     KH_SHA256_ROUNDS16(a, b, c, d, e, f, g, h, w, kb);
   }
 #else
@@ -232,7 +239,7 @@ KH_HD void hash160_job(uint32_t out[5], int job, const fe &x, const fe &y) {
       for (int i = 1; i < 15; i++) w[i] = 0;
       w[15] = 0x208u;
     }
-    sha256_compress(st, w);
+    sha256_compress(st, w, blk ? 2 : (unc ? 0 : 1));
   }
   ripemd160_of_sha(out, st);
 }
