@@ -121,8 +121,6 @@ struct ScanEmit {
   KH_HDM void point_endo(const fe &x, const fe &y, uint64_t batch, uint32_t idx) {
     uint32_t h[5];
     const fe b1 = {KH_BETA}, b2 = {KH_BETA2};
-    fe ny;
-    if (NEED_Y) fe_neg(ny, y);
 #pragma unroll 1
     for (int v = 0; v < 3; v++) {
       fe xv = x;
@@ -140,6 +138,8 @@ struct ScanEmit {
         if (v == 2) fe_mul_sel<OUTLINE_MUL>(xe, x, b1);
         eth_address(h, xe, y);
         probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v));
+        fe ny;                                           // negated on the spot: one fe less alive across the candidate loop
+        fe_neg(ny, y);
         eth_address(h, xv, ny);
         probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v + 1));
       }
@@ -153,7 +153,9 @@ struct ScanEmit {
       if (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {
 #pragma unroll 1
         for (int neg = 0; neg < 2; neg++) {
-          hash160_job<NEED_Y>(h, 2, xv, neg ? ny : y);
+          fe yy = y;
+          if (neg) fe_neg(yy, y);
+          hash160_job<NEED_Y>(h, 2, xv, yy);
           probe(h, KH_KIND_UNCOMP, batch, idx, (uint32_t)(6 + 2 * v + neg));
         }
       }
