@@ -43,6 +43,7 @@ struct kh_ctx {
   kh_bloom_desc bloom_desc{};
   uint8_t *d_bloom = nullptr;
   uint32_t *d_table = nullptr;     // N x 5 BE words
+  size_t table_alloc = 0, bloom_alloc = 0;   // bytes behind d_table / d_bloom
   uint64_t n_targets = 0;
   std::vector<uint8_t> h_table20;  // sorted records (host copy for kh_get_table)
   uint32_t *d_pre = nullptr;       // exact prefix bitmap in front of the bloom (ScanTargets::pre), 2^pre_k bits

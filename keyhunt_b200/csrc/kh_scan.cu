@@ -34,6 +34,14 @@ __global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *g
   }
 }
 
+// exact prefix bitmap over the first k bits of every target record (ScanTargets::pre)
+__global__ void kh_pre_build(uint32_t *pre, uint32_t k, const uint32_t *table_be, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t idx = table_be[5 * i] >> (32 - k);
+  atomicOr(pre + (idx >> 5), 1u << (idx & 31));
+}
+
 __global__ void kh_bloom_build(BloomDev bl, const uint32_t *table_be, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -276,13 +284,21 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
     for (int k = 0; k < 5; k++)
       packed[5 * i + k] = ((uint32_t)p[4 * k] << 24) | ((uint32_t)p[4 * k + 1] << 16) | ((uint32_t)p[4 * k + 2] << 8) | p[4 * k + 3];
   }
-  if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; }
-  if (c->d_bloom) { cudaFree(c->d_bloom); c->d_bloom = nullptr; }
+  // device buffers are kept across calls when the sizes repeat (a caller that re-sends the same target set every step)
   c->have_targets = false;
-  KH_CUDA(c, cudaMalloc(&c->d_table, std::max<size_t>(5 * n, 8) * sizeof(uint32_t)));
+  const size_t table_bytes = std::max<size_t>(5 * n, 8) * sizeof(uint32_t);
+  if (!c->d_table || c->table_alloc != table_bytes) {
+    if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; }
+    KH_CUDA(c, cudaMalloc(&c->d_table, table_bytes));
+    c->table_alloc = table_bytes;
+  }
   if (n) KH_CUDA(c, cudaMemcpyAsync(c->d_table, packed.data(), 5 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   const size_t bloom_alloc = (size_t)((d.bytes + 15) / 16) * 16;
-  KH_CUDA(c, cudaMalloc(&c->d_bloom, bloom_alloc));
+  if (!c->d_bloom || c->bloom_alloc != bloom_alloc) {
+    if (c->d_bloom) { cudaFree(c->d_bloom); c->d_bloom = nullptr; }
+    KH_CUDA(c, cudaMalloc(&c->d_bloom, bloom_alloc));
+    c->bloom_alloc = bloom_alloc;
+  }
   KH_CUDA(c, cudaMemsetAsync(c->d_bloom, 0, bloom_alloc, c->stream));
   if (bloom_bits) {
     KH_CUDA(c, cudaMemcpyAsync(c->d_bloom, bloom_bits, d.bytes, cudaMemcpyHostToDevice, c->stream));
@@ -294,16 +310,21 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
     c->stats.aux_ms += kh_time_end(c);
     c->stats.other_launches += 1;
   }
-  // prefix bitmap (ScanTargets::pre): >= 256 bits per target (fill <= 0.4 %) between 2^16 and 2^32 bits (8 KB .. 512 MB)
+  // prefix bitmap (ScanTargets::pre): >= 256 bits per target (fill <= 0.4 %) between 2^16 and 2^32 bits (8 KB .. 512 MB),
+  // filled on the device from the table that was just uploaded
   {
-    if (c->d_pre) { cudaFree(c->d_pre); c->d_pre = nullptr; }
     uint32_t k = 16;
     if (c->prefilter) while (k < 32 && (1ull << k) < 256ull * n) k++;
-    std::vector<uint32_t> bm((size_t)1 << (k - 5), c->prefilter ? 0u : 0xFFFFFFFFu);
-    for (uint64_t i = 0; i < n; i++) { const uint32_t idx = packed[5 * i] >> (32 - k); bm[idx >> 5] |= 1u << (idx & 31); }
-    KH_CUDA(c, cudaMalloc(&c->d_pre, bm.size() * sizeof(uint32_t)));
-    KH_CUDA(c, cudaMemcpyAsync(c->d_pre, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    KH_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t pre_bytes = (size_t)1 << (k - 3);
+    if (!c->d_pre || c->pre_k != k) {
+      if (c->d_pre) { cudaFree(c->d_pre); c->d_pre = nullptr; }
+      KH_CUDA(c, cudaMalloc(&c->d_pre, pre_bytes));
+    }
+    KH_CUDA(c, cudaMemsetAsync(c->d_pre, c->prefilter ? 0x00 : 0xFF, pre_bytes, c->stream));
+    if (c->prefilter && n) {
+      kh_pre_build<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_pre, k, c->d_table, n);
+      c->stats.other_launches += 1;
+    }
     c->pre_k = k;
   }
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
