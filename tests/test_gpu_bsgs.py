@@ -140,3 +140,30 @@ def test_bsgs_server_variant_base_check(kh, oracle):
             kh.set_option("bsgs_base_check", 0)
     finally:
         oracle.bsgs_free(b)
+
+
+def test_k4096_tables_resident_in_one_gpu(kh, oracle):
+    """bsgs -k 4096 (the reference's own BSGSD.md example: m = 2^34 baby points, 61.75 GB tier-1 bloom + the 64 GB prefix
+    bitmap, everything resident in one B200's HBM): the reference's sizes, sampled baby points are members of tier 1, the
+    puzzle-63 key of that example and keys planted in the first / last window of a 2^64 range are found, a miss is a miss."""
+    kh.bsgs_build(1 << 44, 4096)
+    try:
+        d = kh.bsgs_describe()
+        assert (d.m, d.m2, d.m3, d.aux) == (1 << 34, 1 << 29, 1 << 24, 1024)
+        rnd = random.Random(4096)
+        for j in [1, d.m] + [rnd.randrange(1, d.m + 1) for _ in range(4)]:
+            xb = oracle.pubkey(j)[0].to_bytes(32, "big")
+            bf, desc = kh.bsgs_export(1, xb[0]), d.tier[0]
+            a = oracle.xxh64(xb, 0x59f2815b16f81798)
+            b = oracle.xxh64(xb, a)
+            assert all((bf[(((a + b * i) & (2**64 - 1)) % desc.bits) >> 3] >> ((((a + b * i) & (2**64 - 1)) % desc.bits) & 7)) & 1
+                       for i in range(desc.hashes)), j
+            del bf
+        p63 = 0x7CCE5EFDACCF6808
+        lo, hi = 1 << 64, 1 << 65
+        cases = [(p63, 1 << 62, 1 << 63), (lo + 12345, lo, hi), (hi - 99, lo, hi), (hi + (1 << 50), lo, hi)]
+        for key, a, b in cases:
+            want = key if a <= key < b else None
+            assert kh.bsgs_search(oracle.pubkey(key), a, b) == want, hex(key)
+    finally:
+        kh.bsgs_build(1 << 20, 1)          # give the 126 GB back to the rest of the session
