@@ -143,20 +143,16 @@ struct ScanEmit {
         eth_address(h, xv, ny);
         probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v + 1));
       }
-      if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_BOTH) {
+      if (KIND == KH_SCAN_COMP || KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {
+        // one loop, one call site (= one copy of the hash code in the hot loop): jobs 0,1 = prefixes 02,03 of xv,
+        // jobs 2,3 = uncompressed (xv, y) and (xv, -y)
+        const int j0 = (KIND == KH_SCAN_UNCOMP) ? 2 : 0, j1 = (KIND == KH_SCAN_COMP) ? 2 : 4;
 #pragma unroll 1
-        for (int job = 0; job < 2; job++) {
-          hash160_job<NEED_Y>(h, job, xv, y);
-          probe(h, (uint32_t)job, batch, idx, (uint32_t)(2 * v + job));
-        }
-      }
-      if (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH) {
-#pragma unroll 1
-        for (int neg = 0; neg < 2; neg++) {
+        for (int j = j0; j < j1; j++) {
           fe yy = y;
-          if (neg) fe_neg(yy, y);
-          hash160_job<NEED_Y>(h, 2, xv, yy);
-          probe(h, KH_KIND_UNCOMP, batch, idx, (uint32_t)(6 + 2 * v + neg));
+          if (NEED_Y && j == 3) fe_neg(yy, y);
+          hash160_job<NEED_Y>(h, j < 2 ? j : 2, xv, yy);
+          probe(h, j < 2 ? (uint32_t)j : (uint32_t)KH_KIND_UNCOMP, batch, idx, j < 2 ? (uint32_t)(2 * v + j) : (uint32_t)(6 + 2 * v + (j - 2)));
         }
       }
     }
