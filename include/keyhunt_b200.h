@@ -133,6 +133,9 @@ typedef struct {
   uint64_t points;         /* points (scan) or giant steps (bsgs) or baby steps (build) walked */
   uint64_t walker_threads; /* T of the last walk */
   uint64_t tier1_positives;/* BSGS: tier-1 bloom positives sent to refinement */
+  uint64_t collapsed_batches; /* 1024-point batches whose shared inverse did not exist (centre = +-e*stride*G, i.e. the range
+                                 touches key 0 mod n); the reference's IntGroup::ModInv yields garbage for such a batch
+                                 (SURVEY App. B.11), here it reports nothing and is counted */
 } kh_stats;
 int kh_get_stats(kh_ctx *ctx, kh_stats *out, int reset);
 int kh_device_info(kh_ctx *ctx, char *name, int name_cap, int *sm_count, uint64_t *hbm_bytes);
@@ -140,6 +143,23 @@ int kh_device_info(kh_ctx *ctx, char *name, int name_cap, int *sm_count, uint64_
  * the integer roofline: [0] IADD3, [1] LOP3, [2] SHF, [3] IMAD, [4] IMAD.WIDE.U32.X (fe_mul row),
  * [5] LOP3+IMAD issued together (both integer pipes) */
 int kh_int_peak(kh_ctx *ctx, double out_ops_per_s[6]);
+/* more pipe micro-benchmarks (thread-level ops/s over the whole chip), the evidence behind the choice of multiplier:
+ * [0] IMAD.WIDE.U32 without carry chain, [1] IMAD.HI.U32, [2] DFMA (FP64 pipe), [3] DADD, [4] DFMA + IMAD.WIDE issued
+ * together (do the FP64 and FMA-heavy pipes overlap?), [5] IMAD.WIDE.U32.X + IADD3 together (multiplier + carry work),
+ * [6] FFMA, [7] reserved */
+int kh_pipe_peak(kh_ctx *ctx, double out_ops_per_s[8]);
+/* hash micro-benchmarks in isolation: [0] SHA-256 compressions/s, [1] RIPEMD-160 blocks/s, at blocks_per_sm CTAs of 256 */
+int kh_hash_peak(kh_ctx *ctx, int blocks_per_sm, double out_blocks_per_s[2]);
+
+/* ---- device-side known-answer test of the field layer ---------------------------------------------
+ * Runs one field operation per element ON THE GPU with the very functions the kernels use (the PTX carry-chain bodies of
+ * fe.cuh) — parity tests feed it the reference-generated vectors of Int::ModMulK1 (IntMod.cpp:855), ModSquareK1 (:977),
+ * ModInv (:382), ModAdd (:41), ModSub (:72), ModNeg (:102) and forced edge operands.  a_be / b_be / out_be: n x 32-byte
+ * big-endian values (b is ignored by unary ops; operands of the modular ops must be < P like everywhere on the path).
+ * KH_FE_REDUCE_WIDE reduces the 512-bit value a*2^256 + b, any a and b. */
+enum { KH_FE_MUL = 0, KH_FE_SQR = 1, KH_FE_INV = 2, KH_FE_ADD = 3, KH_FE_SUB = 4, KH_FE_NEG = 5, KH_FE_MUL_OUTLINE = 6,
+       KH_FE_MULWIDE_LO = 7, KH_FE_MULWIDE_HI = 8, KH_FE_SQRWIDE_LO = 9, KH_FE_SQRWIDE_HI = 10, KH_FE_REDUCE_WIDE = 11 };
+int kh_selftest_fe(kh_ctx *ctx, int op, const uint8_t *a_be, const uint8_t *b_be, uint64_t n, uint8_t *out_be);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,11 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 EXPORTS = ["kh_create", "kh_destroy", "kh_last_error", "kh_set_option", "kh_bloom_params", "kh_set_targets",
            "kh_get_bloom", "kh_get_table", "kh_scan", "kh_poll_hits", "kh_derive", "kh_bsgs_build",
            "kh_bsgs_describe", "kh_bsgs_export", "kh_bsgs_import", "kh_bsgs_search", "kh_get_stats",
-           "kh_device_info", "kh_int_peak", "kh_set_vanity"]
+           "kh_device_info", "kh_int_peak", "kh_set_vanity", "kh_pipe_peak", "kh_hash_peak", "kh_selftest_fe"]
+
+# kh_selftest_fe ops (include/keyhunt_b200.h)
+FE_MUL, FE_SQR, FE_INV, FE_ADD, FE_SUB, FE_NEG, FE_MUL_OUTLINE = 0, 1, 2, 3, 4, 5, 6
+FE_MULWIDE_LO, FE_MULWIDE_HI, FE_SQRWIDE_LO, FE_SQRWIDE_HI, FE_REDUCE_WIDE = 7, 8, 9, 10, 11
 
 
 class KhError(RuntimeError):
@@ -66,7 +70,7 @@ class BsgsDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("walk_ms", C.c_double), ("setup_ms", C.c_double), ("aux_ms", C.c_double),
                 ("walk_launches", C.c_uint64), ("other_launches", C.c_uint64), ("points", C.c_uint64),
-                ("walker_threads", C.c_uint64), ("tier1_positives", C.c_uint64)]
+                ("walker_threads", C.c_uint64), ("tier1_positives", C.c_uint64), ("collapsed_batches", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -133,6 +137,9 @@ def load_library(path=None):
     L.kh_get_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
     L.kh_device_info.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(u64)]
     L.kh_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.kh_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.kh_hash_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.kh_selftest_fe.argtypes = [vp, C.c_int, u8p, u8p, u64, vp]
     for name in EXPORTS:
         if name not in ("kh_destroy", "kh_last_error"):
             getattr(L, name).restype = C.c_int
@@ -228,14 +235,25 @@ class KeyHunt:
         self._ck(self._lib.kh_scan(self._h, _be32(start), _be32(stride), n_points))
 
     def poll_hits(self, max_hits=4096):
+        """Drains the hits of the scans since the last poll.  If the device hit buffer overflowed (KH_EOVERFLOW) the hits
+        that were kept are still returned: the overflow is raised as KhError carrying them in ``.hits``."""
         out = []
+        overflow = None
         while True:
             arr = (_Hit * max_hits)()
             n = C.c_int()
-            self._ck(self._lib.kh_poll_hits(self._h, arr, max_hits, C.byref(n)))
+            rc = self._lib.kh_poll_hits(self._h, arr, max_hits, C.byref(n))
             out.extend(Hit(arr[i]) for i in range(n.value))
+            if rc == -5:                       # KH_EOVERFLOW: kh_poll_hits has already handed over (and erased) these hits
+                overflow = KhError(rc, self._lib.kh_last_error(self._h).decode())
+            elif rc:
+                self._ck(rc)
             if n.value < max_hits:
-                return out
+                break
+        if overflow is not None:
+            overflow.hits = out
+            raise overflow
+        return out
 
     def derive(self, keys):
         keys = list(keys)
@@ -275,6 +293,28 @@ class KeyHunt:
         arr = (C.c_double * 6)()
         self._ck(self._lib.kh_int_peak(self._h, arr))
         return dict(zip(["iadd3", "lop3", "shf", "imad", "imad_wide", "lop3_imad_mix"], [float(x) for x in arr]))
+
+    def pipe_peak(self):
+        """more measured pipe rates (thread-ops/s, whole chip): the evidence behind the choice of multiplier"""
+        arr = (C.c_double * 8)()
+        self._ck(self._lib.kh_pipe_peak(self._h, arr))
+        return dict(zip(["imad_wide_nocarry", "imad_hi", "dfma", "dadd", "dfma_plus_imad_wide", "imad_wide_plus_iadd3", "ffma"],
+                        [float(x) for x in arr]))
+
+    def hash_peak(self, blocks_per_sm=2):
+        arr = (C.c_double * 2)()
+        self._ck(self._lib.kh_hash_peak(self._h, blocks_per_sm, arr))
+        return {"sha256_compressions_per_s": float(arr[0]), "ripemd160_blocks_per_s": float(arr[1])}
+
+    def selftest_fe(self, op, a, b=None):
+        """one field operation per element ON THE DEVICE (fe.cuh's PTX bodies); a, b: lists of ints -> list of ints"""
+        a = list(a)
+        b = list(b) if b is not None else [0] * len(a)
+        if len(a) != len(b):
+            raise ValueError("operand lists differ in length")
+        out = C.create_string_buffer(max(1, 32 * len(a)))
+        self._ck(self._lib.kh_selftest_fe(self._h, op, b"".join(_be32(x) for x in a), b"".join(_be32(x) for x in b), len(a), out))
+        return [int.from_bytes(out.raw[32 * i:32 * i + 32], "big") for i in range(len(a))]
 
     def stats(self, reset=False):
         s = Stats()

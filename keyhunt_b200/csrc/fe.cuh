@@ -414,6 +414,23 @@ void fe_inv(fe &r, const fe &a) {
   fe_sqr_n_cold(t, t, 2); fe_mul_cold(r, t, a);
 }
 
+// Inversion with operands in registers: fe_inv takes references, which makes its arguments address-taken locals of the
+// caller (stack traffic at every use inside the walk's hot loop); the by-value wrapper keeps them in registers.
+#if defined(__CUDACC__)
+static __device__ __noinline__ fe fe_inv_ol(fe a) {
+  fe r;
+  fe_inv(r, a);
+  return r;
+}
+#endif
+KH_HD void fe_inv_reg(fe &r, const fe &a) {
+#if defined(__CUDA_ARCH__)
+  r = fe_inv_ol(a);
+#else
+  fe_inv(r, a);
+#endif
+}
+
 // ---- (de)serialisation -------------------------------------------------------------------------------
 // 32-byte big-endian string (Int::Get32Bytes, Int.cpp:308) <-> limbs
 KH_HD void fe_from_be(fe &r, const uint8_t *b) {

@@ -80,6 +80,101 @@ extern "C" int kh_int_peak(kh_ctx *c, double out_ops_per_s[6]) {
   return KH_OK;
 }
 
+// ---- more pipes: what a different multiplier could be built from ("the multiplier") -------------------
+// KIND 0 IMAD.WIDE.U32 (64-bit accumulate, no carry chain)   1 IMAD.HI.U32   2 DFMA   3 DADD
+//      4 DFMA + IMAD.WIDE per chain step (FP64 pipe and FMA-heavy pipe together)
+//      5 fe_mul row (4 x IMAD.WIDE.U32.X) + 4 IADD3 (multiplier + the carry/reduction work that shares issue slots)
+//      6 FFMA
+template <int KIND>
+__global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t seed) {
+  uint64_t w[PEAK_CHAINS];
+  uint32_t a[PEAK_CHAINS], b[PEAK_CHAINS];
+  double d[PEAK_CHAINS];
+  float f[PEAK_CHAINS];
+#pragma unroll
+  for (int i = 0; i < PEAK_CHAINS; i++) {
+    a[i] = seed + threadIdx.x * 977u + i; b[i] = (seed * 31u + blockIdx.x + i * 7u) | 1u;
+    w[i] = ((uint64_t)a[i] << 32) | b[i];
+    d[i] = 1.0 + 1e-9 * (double)(a[i] & 1023u);
+    f[i] = 1.0f + 1e-6f * (float)(a[i] & 1023u);
+  }
+  const double dm = 1.0 + 1e-12 * (double)(seed & 7u), da = 1e-15 * (double)(threadIdx.x & 3u);
+  const float fm = 1.0f + 1e-7f * (float)(seed & 7u), fa = 1e-9f * (float)(threadIdx.x & 3u);
+  uint32_t row[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) row[i][k] = seed + 9 * i + k + threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; i++) {
+      if (KIND == 0) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
+      } else if (KIND == 1) {
+        asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 2) {
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dm), "d"(da));
+      } else if (KIND == 3) {
+        asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(da));
+      } else if (KIND == 4) {
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dm), "d"(da));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
+      } else if (KIND == 5) {
+        if (i < 4) kh::kh_mad_row(row[i], a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], row[i][0] | 1u);
+        if (i >= 4 && i < 8) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(b[4 * (i - 4) + k]) : "r"(a[i]), "r"(it));
+        }
+      } else {
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fm), "f"(fa));
+      }
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < PEAK_CHAINS; i++) r ^= a[i] ^ b[i] ^ (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32) ^ (uint32_t)__double2loint(d[i]) ^ __float_as_uint(f[i]);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) r ^= row[i][k];
+  if (r == 0x12345678u) out[0] = r;
+}
+
+template <int KIND>
+static double run_pipe(kh_ctx *c, uint32_t *d_out, int ops_per_step) {
+  const int blocks = c->sm_count * 8;
+  kh_pipe_kernel<KIND><<<blocks, 256, 0, c->stream>>>(d_out, 12345u);
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    kh_time_begin(c);
+    kh_pipe_kernel<KIND><<<blocks, 256, 0, c->stream>>>(d_out, 12345u + rep);
+    const double ms = kh_time_end(c);
+    const double ops = (double)blocks * 256.0 * PEAK_ITERS * PEAK_CHAINS * ops_per_step;
+    best = std::max(best, ops / (ms * 1e-3));
+  }
+  return best;
+}
+
+extern "C" int kh_pipe_peak(kh_ctx *c, double out[8]) {
+  if (!c || !out) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  uint32_t *d_out = nullptr;
+  KH_CUDA(c, cudaMalloc(&d_out, 64));
+  out[0] = run_pipe<0>(c, d_out, 1);
+  out[1] = run_pipe<1>(c, d_out, 1);
+  out[2] = run_pipe<2>(c, d_out, 1);
+  out[3] = run_pipe<3>(c, d_out, 1);
+  out[4] = run_pipe<4>(c, d_out, 2);
+  out[5] = run_pipe<5>(c, d_out, 2);   // 16 IMAD.WIDE.X + 16 IADD3 per loop trip
+  out[6] = run_pipe<6>(c, d_out, 1);
+  out[7] = 0;
+  cudaFree(d_out);
+  c->stats.other_launches += 28;
+  KH_CUDA(c, cudaGetLastError());
+  return KH_OK;
+}
+
 // ---- hash micro-benchmarks: SHA-256 compressions / RIPEMD-160 blocks per second in isolation -----------
 template <int WHICH>
 __global__ void __launch_bounds__(256) kh_hash_bench(uint32_t *out, uint32_t seed, int iters) {

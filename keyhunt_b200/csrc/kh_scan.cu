@@ -195,7 +195,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -438,6 +438,20 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   bool stride_zero = true;
   for (int i = 0; i < 8; i++) stride_zero &= (ws.s.v[i] == 0);
   if (stride_zero) return kh_fail(c, KH_EINVAL, "stride is zero");
+  // scalars are plain 256-bit integers on the device (u256_add_mul64 works mod 2^256, k*G needs no reduction mod n):
+  // the largest one a scan forms is start + stride*(n_points + T*1024) (the hop W = T*1024*S); refuse ranges where
+  // that wraps instead of walking wrong points
+  {
+    unsigned __int128 carry = 0;
+    const uint64_t reach = n_points + T * (uint64_t)KH_GRP;
+    bool wraps = false;
+    for (int i = 0; i < 8; i++) {
+      carry += (unsigned __int128)ws.s.v[i] * reach + ws.k0.v[i];
+      carry >>= 32;
+    }
+    wraps = carry != 0;
+    if (wraps) return kh_fail(c, KH_EINVAL, "start + stride*n_points reaches 2^256");
+  }
   ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
   rc = kh_run_setup(c, ws);
   if (rc) return rc;
@@ -453,7 +467,7 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
 
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
-  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0; wp.flags = c->d_flags;
 
   kh_time_begin(c);
   uint64_t launches = 0;
@@ -482,9 +496,15 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   c->stats.walker_threads = T;
 
   // collect raw hits of this scan and convert them while start/stride are at hand
-  uint32_t count = 0;
+  uint32_t count = 0, wflags[2] = {0, 0};
   KH_CUDA(c, cudaMemcpyAsync(&count, c->d_hit_count, sizeof(count), cudaMemcpyDeviceToHost, c->stream));
+  KH_CUDA(c, cudaMemcpyAsync(wflags, c->d_flags, sizeof(wflags), cudaMemcpyDeviceToHost, c->stream));
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (wflags[0] | wflags[1]) {
+    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(uint32_t), c->stream));
+    c->stats.collapsed_batches += wflags[1];
+    if (wflags[0]) return kh_fail(c, KH_EINVAL, "a walker reached the point at infinity (range touches key 0 mod n)");
+  }
   if (count) {
     if (count > c->hits_alloc) { c->overflowed = true; count = c->hits_alloc; }
     std::vector<RawHit> raw(count);
@@ -498,7 +518,12 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
     });
     // keyfound = index*stride + start (keyhunt.cpp:3625-3627)
     std::vector<u256> keys(count);
-    for (uint32_t i = 0; i < count; i++) u256_add_mul64(keys[i], ws.k0, ws.s, raw[i].batch * KH_GRP + raw[i].idx);
+    for (uint32_t i = 0; i < count; i++) {
+      u256_add_mul64(keys[i], ws.k0, ws.s, raw[i].batch * KH_GRP + raw[i].idx);
+      const uint32_t order[8] = KH_N;            // a chunk that runs past n: report the key mod n (< 2^256 < 2n: one subtraction)
+      uint32_t d[8];
+      if (!kh_sub8(d, keys[i].v, order)) for (int l = 0; l < 8; l++) keys[i].v[l] = d[l];
+    }
     std::vector<DevKeyInfo> info;
     rc = derive_dev(c, keys, info);
     if (rc) return rc;

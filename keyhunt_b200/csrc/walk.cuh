@@ -42,6 +42,7 @@ struct WalkParams {
   uint64_t n_batches;     // batches in the whole range; batch b is processed iff b < n_batches
   uint32_t steps;         // steps of this launch
   uint32_t pad;
+  uint32_t *flags;        // [0] bit 0: a walker reached the point at infinity; [1]: batches that collapsed (see walk_batches)
 };
 
 KH_HD void tab_load(fe &gx, fe &gy, const uint32_t *tab, int e) {
@@ -85,9 +86,32 @@ KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
   a.v[0] = lo.x; a.v[1] = lo.y; a.v[2] = lo.z; a.v[3] = lo.w; a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
 }
 
+KH_HD void walk_flag_or(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+KH_HD void walk_flag_inc(uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, 1u);
+#else
+  (*p)++;
+#endif
+}
 // Walks `steps` batches for walker thread t.  `tab` is the table in shared memory (device) or plain
 // memory (host test build).  For each point calls emit.point(x, y, batch, idx) where key index in the
 // range is batch*1024 + idx; y is valid only if Emit::NEED_Y.
+//
+// Zero differences.  A dx_e = 0 makes the shared product zero, and fe_inv(0) = 0 (like Int::ModInv): every slope of the
+// batch is then 0 and its points are garbage — exactly what IntGroup::ModInv does to the reference's batch when its centre
+// is +-e*S (a range touching key 0 mod n); the centre itself (pts[512]) is still right in both.  Two
+// things the reference does not have and that therefore must not go wrong here:
+//   * the hop entry: a centre equal to W (`-r 200:...` puts walker T-1 there) would zero the product although the
+//     reference's batch is fine -> the forward pass is redone without entry 0 (cold);
+//   * the centre move: it must never be computed from a zero or missing inverse -> it gets an inverse of its own, or the
+//     tangent when C = W, and raises flags[0] when C = -W (point at infinity) (cold).
 template <class Emit>
 KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
   constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
@@ -110,24 +134,35 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
+    if (fe_is_zero(acc)) {                           // cold
+      fe gx0;
+      tab_load_x(gx0, tab, 0);
+      if (fe_eq(gx0, px)) {                          // the hop entry alone may be the culprit: batch product without it
+        fe_set_u32(acc, 1);
+#pragma unroll 1
+        for (int e = 0; e < KH_TAB_ENTRIES; e++) {
+          if (e > 0) { fe gx, dx; tab_load_x(gx, tab, e); fe_sub(dx, gx, px); fe_mul_cold(acc, acc, dx); }
+          if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
+        }
+      }
+      if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
+    }
     fe inv;
-    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move)
+    fe_inv_reg(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1
-    for (int e = KH_TAB_ENTRIES - 1; e >= 0; e--) {
+    for (int e = KH_TAB_ENTRIES - 1; e >= 1; e--) {
       fe gx, gy, dinv;
       tab_load(gx, gy, tab, e);
-      if (e > 0) {
+      {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
         fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
         fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
-      } else {
-        dinv = inv;
       }
-      if (Emit::PAIRS && e != 0 && e != KH_HALF) {
+      if (Emit::PAIRS && e != KH_HALF) {
         // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
         // emitter, the bloom probes of both points in flight at the same time (memory-level parallelism)
         fe dyp, dym, sp, sm, xp, xm, c;
@@ -144,37 +179,50 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       }
 #pragma unroll 1
       for (int sgn = 0; sgn < 2; sgn++) {
-        if (e == KH_HALF && sgn == 0) continue;        // +512*S belongs to the next batch (pts[0] there)
         fe x3, y3;
         uint32_t idx;
-        bool do_emit = true;
-        if (e == 0 && sgn == 0) {                       // the centre itself
-          x3 = px; y3 = py; idx = KH_HALF;
+        if (e == KH_HALF && sgn == 0) {                 // +512*S belongs to the next batch (pts[0] there): this slot
+          x3 = px; y3 = py; idx = KH_HALF;              // carries the centre itself instead
         } else {
           fe s, dy, s2;
-          if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
+          if (sgn == 0) fe_sub(dy, gy, py);             // C + e*S
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
           fe_mul_sel<OL>(s, dy, dinv);
           if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
           fe_sub(x3, s2, px);
           fe_sub(x3, x3, gx);
-          if (e == 0) {                                 // new centre: always needs y
-            fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
-            px = x3; py = y3;
-            do_emit = false;
-            idx = 0;
+          if (Emit::NEED_Y) {
+            if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
+            else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
           } else {
-            if (Emit::NEED_Y) {
-              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
-              else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
-            } else {
-              y3 = py;
-            }
-            idx = (sgn == 0) ? (uint32_t)(KH_HALF + e) : (uint32_t)(KH_HALF - e);
+            y3 = py;
           }
+          idx = (sgn == 0) ? (uint32_t)(KH_HALF + e) : (uint32_t)(KH_HALF - e);
         }
-        if (do_emit) emit.point(x3, y3, batch, idx);
+        emit.point(x3, y3, batch, idx);
       }
+    }
+
+    // ---- centre move C + W: what is left of inv is 1/dx_0 (once per batch: the shared out-of-line multiplier) ------
+    {
+      fe gx, gy, dx, dy, s, s2, x3, y3;
+      tab_load(gx, gy, tab, 0);
+      fe_sub(dx, gx, px);
+      fe_sub(dy, gy, py);
+      if (fe_is_zero(inv) || fe_is_zero(dx)) {        // cold: collapsed batch, or the centre is +-W
+        if (fe_is_zero(dx)) {
+          if (!fe_is_zero(dy)) { walk_flag_or(wp.flags, 1u); break; }      // C = -W: the next centre is the point at infinity
+          fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2);   // C = W: tangent, slope 3x^2 / 2y
+          fe_add(dx, py, py);
+        }
+        fe_inv_reg(inv, dx);
+      }
+      fe_mul_cold(s, dy, inv);
+      fe_mul_cold(s2, s, s);
+      fe_sub(x3, s2, px);
+      fe_sub(x3, x3, gx);
+      fe_sub(y3, gx, x3); fe_mul_cold(y3, y3, s); fe_sub(y3, y3, gy);
+      px = x3; py = y3;
     }
   }
 #pragma unroll

@@ -357,25 +357,56 @@ static void write_scan_hit(kh_ctx *c, const kh_hit &h) {
   fflush(stdout);
 }
 
-// one host thread per GPU: the loop of thread_process (keyhunt.cpp:3309-3858) with the batches on the device
+// one host thread per GPU: the loop of thread_process (keyhunt.cpp:3309-3858) with the batches on the device.
+// A worker of the reference claims ONE chunk of N_SEQUENTIAL_MAX keys per turn; one such chunk (the reference's usual
+// -n 0x100000 .. 0x1000000) is far too little work for a GPU call (606,208 walkers x 1024 keys fill one step), so a
+// worker claims a RUN of contiguous chunks under the same lock and scans it with one kh_scan.  With stride 1 a run of
+// chunks is one arithmetic progression and every claimed chunk is still scanned whole (the overshoot rule of
+// keyhunt.cpp:3314-3324), so the scanned key set and the hit records are exactly the reference's.  With a stride the
+// reference still advances its cursor by N_SEQUENTIAL_MAX per chunk (:3323), so consecutive chunks are NOT one
+// progression and are scanned one by one.
+static int n_scan_workers = 1;
+static const uint64_t RUN_POINTS = 1ULL << 32;                             // keys per kh_scan the workers aim at
 static void scan_worker(kh_ctx *c, int id) {
+  const bool stride_one = (u_cmp(stride_v, u_from_u64(1)) == 0);
   for (;;) {
     U256 key;
+    uint64_t chunks = 0;
     {
       std::lock_guard<std::mutex> g(write_random);
       if (u_cmp(n_range_start, n_range_end) >= 0) break;                  // keyhunt.cpp:3314
       key = n_range_start;
-      n_range_start = u_add(key, u_from_u64(N_SEQUENTIAL_MAX));           // :3323 Add(N_SEQUENTIAL_MAX), whatever the stride
+      uint64_t want = 1;
+      if (stride_one && N_SEQUENTIAL_MAX < RUN_POINTS) {
+        want = RUN_POINTS / N_SEQUENTIAL_MAX;
+        // leave the other GPUs their share when what is left of the range is small
+        const U256 left = u_sub(n_range_end, n_range_start);
+        bool small = true;
+        for (int i = 0; i < 24; i++) small = small && left.b[i] == 0;
+        if (small) {
+          uint64_t l = 0;
+          for (int i = 24; i < 32; i++) l = (l << 8) | left.b[i];
+          const uint64_t left_chunks = l / N_SEQUENTIAL_MAX + ((l % N_SEQUENTIAL_MAX) ? 1 : 0);
+          const uint64_t share = (left_chunks + (uint64_t)n_scan_workers - 1) / (uint64_t)n_scan_workers;
+          if (share < want) want = share ? share : 1;
+        }
+      }
+      while (chunks < want && u_cmp(n_range_start, n_range_end) < 0) {     // every claim is the reference's: test, then Add(N_SEQUENTIAL_MAX) (:3323)
+        if (!FLAGQUIET) { if (FLAGMATRIX) printf("Base key: %s thread %i\n", u_hex(n_range_start).c_str(), id); else printf("\rBase key: %s     \r", u_hex(n_range_start).c_str()); }
+        n_range_start = u_add(n_range_start, u_from_u64(N_SEQUENTIAL_MAX));
+        chunks++;
+      }
+      if (!FLAGQUIET) fflush(stdout);
     }
-    if (!FLAGQUIET) { if (FLAGMATRIX) printf("Base key: %s thread %i\n", u_hex(key).c_str(), id); else printf("\rBase key: %s     \r", u_hex(key).c_str()); fflush(stdout); }
-    if (kh_scan(c, key.b, stride_v.b, N_SEQUENTIAL_MAX) != KH_OK) die("[E] %s", kh_last_error(c));
-    total_points += N_SEQUENTIAL_MAX;
+    const uint64_t n_points = chunks * N_SEQUENTIAL_MAX;
+    if (kh_scan(c, key.b, stride_v.b, n_points) != KH_OK) die("[E] %s", kh_last_error(c));
+    total_points += n_points;
     kh_hit hits[64];
     int n = 0;
     do {
       int rc = kh_poll_hits(c, hits, 64, &n);
       if (rc != KH_OK && rc != KH_EOVERFLOW) die("[E] %s", kh_last_error(c));
-      if (rc == KH_EOVERFLOW) fprintf(stderr, "\n[W] more hits in the chunk at %s than the device hit buffer holds: the excess was DROPPED; use a smaller -n\n", u_hex(key).c_str());
+      if (rc == KH_EOVERFLOW) fprintf(stderr, "\n[W] more hits in the chunks at %s than the device hit buffer holds: the excess was DROPPED; use a smaller -n\n", u_hex(key).c_str());
       for (int i = 0; i < n; i++) write_scan_hit(c, hits[i]);
     } while (n == 64);
   }
@@ -719,6 +750,7 @@ int main(int argc, char **argv) {
     }
     fflush(stdout);
     std::vector<std::thread> th;
+    n_scan_workers = (int)gpus.size();
     for (size_t g = 0; g < gpus.size(); g++) th.emplace_back(scan_worker, gpus[g], (int)g);
     for (auto &t : th) t.join();
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -555,6 +555,9 @@ int kho_bloom_check(void *h, const void *buf, int len) { return bloom_check_add(
 void kho_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(&x, a); fe_from_be(&y, b); fe_mul(&r, &x, &y); fe_to_be(out, &r); }
 void kho_fe_sqr(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(&x, a); fe_sqr(&r, &x); fe_to_be(out, &r); }
 void kho_fe_inv(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(&x, a); fe_inv(&r, &x); fe_to_be(out, &r); }
+void kho_fe_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(&x, a); fe_from_be(&y, b); fe_add(&r, &x, &y); fe_to_be(out, &r); }
+void kho_fe_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(&x, a); fe_from_be(&y, b); fe_sub(&r, &x, &y); fe_to_be(out, &r); }
+void kho_fe_neg(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(&x, a); fe_neg(&r, &x); fe_to_be(out, &r); }
 void kho_pubkey(const uint8_t key[32], uint8_t xy[64]) { fe k; ge p; fe_from_be(&k, key); ge_scalar_mul(&p, &GE_G, &k); fe_to_be(xy, &p.x); fe_to_be(xy + 32, &p.y); }
 static void ge_from_be(ge *p, const uint8_t xy[64]) { fe_from_be(&p->x, xy); fe_from_be(&p->y, xy + 32); }
 static void ge_to_be(uint8_t xy[64], const ge *p) { fe_to_be(xy, &p->x); fe_to_be(xy + 32, &p->y); }

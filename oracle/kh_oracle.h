@@ -25,6 +25,9 @@ extern "C" {
 void kho_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 void kho_fe_sqr(const uint8_t a[32], uint8_t out[32]);
 void kho_fe_inv(const uint8_t a[32], uint8_t out[32]);      /* inv(0) = 0 like Int::ModInv */
+void kho_fe_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);   /* Int::ModAdd IntMod.cpp:51 */
+void kho_fe_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);   /* Int::ModSub IntMod.cpp:97 */
+void kho_fe_neg(const uint8_t a[32], uint8_t out[32]);                        /* Int::ModNeg IntMod.cpp:105, canonical */
 
 /* ---- L1 group (SECP256K1.cpp:205 ComputePublicKey, :455 AddDirect) ---------------------------- */
 void kho_pubkey(const uint8_t key[32], uint8_t xy[64]);

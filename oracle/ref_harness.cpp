@@ -76,6 +76,34 @@ void khr_fe_inv(const uint8_t a[32], uint8_t out[32]) {
   x.Get32Bytes(out);
 }
 
+// Int::ModAdd(a, b) / ModSub(a, b) / ModNeg (IntMod.cpp:51, :97, :105)
+void khr_fe_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+  ensure_init();
+  Int x, y, r;
+  x.Set32Bytes((unsigned char *)a);
+  y.Set32Bytes((unsigned char *)b);
+  r.ModAdd(&x, &y);
+  canon(r);
+  r.Get32Bytes(out);
+}
+void khr_fe_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+  ensure_init();
+  Int x, y, r;
+  x.Set32Bytes((unsigned char *)a);
+  y.Set32Bytes((unsigned char *)b);
+  r.ModSub(&x, &y);
+  canon(r);
+  r.Get32Bytes(out);
+}
+void khr_fe_neg(const uint8_t a[32], uint8_t out[32]) {
+  ensure_init();
+  Int x;
+  x.Set32Bytes((unsigned char *)a);
+  x.ModNeg();
+  canon(x);
+  x.Get32Bytes(out);
+}
+
 void khr_pubkey(const uint8_t key[32], uint8_t xy[64]) {
   ensure_init();
   Int k;

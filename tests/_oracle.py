@@ -59,6 +59,9 @@ class _Lib:
         self._sig("fe_mul", None, [u8p, u8p, u8p])
         self._sig("fe_sqr", None, [u8p, u8p])
         self._sig("fe_inv", None, [u8p, u8p])
+        self._sig("fe_add", None, [u8p, u8p, u8p])
+        self._sig("fe_sub", None, [u8p, u8p, u8p])
+        self._sig("fe_neg", None, [u8p, u8p])
         self._sig("pubkey", None, [u8p, u8p])
         self._sig("add_direct", None, [u8p, u8p, u8p])
         self._sig("batch_points", None, [u8p, u8p, C.c_int, u8p])
@@ -84,6 +87,15 @@ class _Lib:
     # ---- primitives -------------------------------------------------------------------------
     def fe_mul(self, a, b):
         o = C.create_string_buffer(32); self._fe_mul(be32(a), be32(b), o); return int.from_bytes(o.raw, "big")
+
+    def fe_add(self, a, b):
+        o = C.create_string_buffer(32); self._fe_add(be32(a), be32(b), o); return int.from_bytes(o.raw, "big")
+
+    def fe_sub(self, a, b):
+        o = C.create_string_buffer(32); self._fe_sub(be32(a), be32(b), o); return int.from_bytes(o.raw, "big")
+
+    def fe_neg(self, a):
+        o = C.create_string_buffer(32); self._fe_neg(be32(a), o); return int.from_bytes(o.raw, "big")
 
     def fe_sqr(self, a):
         o = C.create_string_buffer(32); self._fe_sqr(be32(a), o); return int.from_bytes(o.raw, "big")

@@ -23,6 +23,14 @@ void ds_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x
 void ds_fe_sqr(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_sqr(r, x); fe_to_be(out, r); }
 void ds_fe_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_add(r, x, y); fe_to_be(out, r); }
 void ds_fe_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_sub(r, x, y); fe_to_be(out, r); }
+void ds_fe_neg(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_neg(r, x); fe_to_be(out, r); }
+// (hi * 2^256 + lo) mod P for any 512-bit value (the KH_FE_REDUCE_WIDE op of kh_selftest_fe)
+void ds_fe_reduce_wide(const uint8_t hi[32], const uint8_t lo[32], uint8_t out[32]) {
+  fe h, l, r; fe_from_be(h, hi); fe_from_be(l, lo);
+  uint32_t w[16];
+  for (int i = 0; i < 8; i++) { w[i] = l.v[i]; w[8 + i] = h.v[i]; }
+  fe_reduce_wide(r, w); fe_to_be(out, r);
+}
 void ds_fe_inv(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_inv(r, x); fe_to_be(out, r); }
 
 void ds_pubkey(const uint8_t key[32], uint8_t xy[64]) {
@@ -54,6 +62,10 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
   }
   scratch.resize((size_t)1024 * ws.T);
 }
+
+// WalkParams::flags of the emulated launches: [0] walker-at-infinity bit, [1] collapsed batches
+static uint32_t g_walk_flags[2] = {0, 0};
+void ds_walk_flags(uint32_t out[2], int reset) { out[0] = g_walk_flags[0]; out[1] = g_walk_flags[1]; if (reset) g_walk_flags[0] = g_walk_flags[1] = 0; }
 
 // -m vanity for the next ds_scan calls: van = 2048-word prefix bitmap + n x (A[5], B[5]) big-endian words (ScanTargets::van); n = 0 switches it off
 static const uint32_t *g_van = nullptr;
@@ -99,7 +111,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
 
   WalkParams wp;
   wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
-  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch; wp.pad = 0; wp.flags = g_walk_flags;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;
     for (uint64_t t = 0; t < T; t++) {
@@ -157,7 +169,7 @@ void ds_walk_dump(const uint8_t start[32], const uint8_t stride[32], uint64_t n_
   make_walk(ws, gtab, centers, scratch);
   WalkParams wp;
   wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
-  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch; wp.pad = 0; wp.flags = g_walk_flags;
   DumpEmit e; e.out = out;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;

@@ -49,7 +49,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(K._Hit) == 32 * 3 + 20 + 4 + 8
     assert C.sizeof(K._KeyInfo) == 64 + 60 + 4
     assert C.sizeof(K.BsgsDesc) == 40 + 3 * 32
-    assert C.sizeof(K.Stats) == 3 * 8 + 5 * 8
+    assert C.sizeof(K.Stats) == 3 * 8 + 6 * 8
 
 
 def test_product_does_not_touch_oracle():

@@ -91,6 +91,45 @@ def test_walk_geometry(ds, oracle, start, stride, nb, T, spl):
         assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(start + b * 1024 * stride, stride, True)
 
 
+def _walk_flags(ds):
+    fl = (C.c_uint32 * 2)()
+    ds.ds_walk_flags(fl, 1)
+    return list(fl)
+
+
+def test_walk_centre_on_the_hop_point(ds, oracle):
+    """start = 512, stride 1, T walkers: walker T-1 starts with its centre ON W = T*1024*G, so the hop's difference is zero
+    (ADVICE r1).  The reference has no such hop: its batch is fine, and so must ours be; the centre then moves by the
+    tangent and the walker's later batches are right as well."""
+    T, nb = 4, 12
+    out = C.create_string_buffer(nb * 65536)
+    _walk_flags(ds)
+    ds.ds_walk_dump(be32(512), be32(1), nb, T, 2, out)
+    assert _walk_flags(ds) == [0, 0]
+    for b in range(1, nb):
+        assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(512 + b * 1024, 1, True), b
+    # batch 0 has its centre on 1024*G = the reference's own next-start delta (_2Gn, keyhunt.cpp:3448): the REFERENCE's batch
+    # collapses there (SURVEY App. B.11); ours holds the true points (a superset of what the reference can find)
+    for i in (0, 1, 511, 512, 513, 1023):
+        x, y = oracle.pubkey(512 + i)
+        assert out.raw[64 * i:64 * i + 64] == be32(x) + be32(y)
+    assert out.raw[:65536] != oracle.batch_points(512, 1, True)
+
+
+def test_walk_batch_without_inverse_matches_the_reference(ds, oracle):
+    """a range that runs over key 0 (mod n): the centre of a batch is +-512*G, one difference is zero, no shared inverse
+    exists.  IntGroup::ModInv then yields zeros and the reference's 1023 non-centre points are deterministic garbage
+    (SURVEY App. B.11); the same garbage comes out here, the batch is counted, and the walker's next batches are right."""
+    start, T, nb = N_ORDER - 1024, 2, 6
+    out = C.create_string_buffer(nb * 65536)
+    _walk_flags(ds)
+    ds.ds_walk_dump(be32(start), be32(1), nb, T, 3, out)
+    assert _walk_flags(ds) == [0, 2]
+    for b in range(nb):
+        base = start + b * 1024
+        assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(base % N_ORDER if b else base, 1, True), b
+
+
 KINDS = {"xpoint": (0, MODE_XPOINT, CRYPTO_BTC, SEARCH_COMPRESS), "comp": (1, MODE_RMD160, CRYPTO_BTC, SEARCH_COMPRESS),
          "uncomp": (2, MODE_RMD160, CRYPTO_BTC, SEARCH_UNCOMPRESS), "both": (3, MODE_ADDRESS, CRYPTO_BTC, SEARCH_BOTH),
          "eth": (4, MODE_ADDRESS, CRYPTO_ETH, SEARCH_COMPRESS)}

@@ -173,3 +173,30 @@ def test_cli_bsgs_window_pickers_identical_to_reference(dirs, oracle, mode):
     assert records(g, 2) == records(r, 2), (records(g, 2), records(r, 2))
     found = {int(rec.split("|")[0].split()[-1], 16) for rec in records(g, 2)}
     assert set(inside) <= found
+
+
+def test_cli_small_n_keeps_the_gpu_full(dirs, kh):
+    """`-n 0x1000000` (the chunk size SURVEY §8d prescribes for the CPU run) used to give the GPU 16,384 of
+    606,208 walkers per kh_scan.  Contiguous chunk claims are now scanned as one run: the rate must be within 3 % of the
+    default `-n 0x100000000`, and the records identical (C2-like: rmd160 -l both, 1,024 targets, 12 planted, 2^34 keys)."""
+    import random
+    import re
+    g, r = dirs
+    start, n = 0x2000000000000000, 1 << 34
+    rnd = random.Random(77)
+    idxs = sorted({0, n - 1} | {rnd.randrange(n) for _ in range(10)})
+    infos = kh.derive([start + i for i in idxs])
+    recs = [(inf.h160_uncomp if j % 2 else inf.h160_comp) for j, inf in enumerate(infos)] + [rnd.randbytes(20) for _ in range(1012)]
+    rates, found = {}, {}
+    for d, nflag in ((g, "0x1000000"), (r, "0x100000000")):
+        fn = os.path.join(d, "t.rmd")
+        open(fn, "w").write("".join(x.hex() + "\n" for x in recs))
+        rc, out = run(CLI, ["-m", "rmd160", "-f", fn, "-r", "%x:%x" % (start, start + n), "-l", "both", "-n", nflag, "-q", "-t", "1"], d)
+        assert rc == 0 and "End" in out, out[-2000:]
+        m = re.search(r"Total (\d+) keys in \d+ seconds: .*\((\d+) keys/s\)", out)
+        assert m and int(m.group(1)) == n, out[-500:]
+        rates[nflag], found[nflag] = int(m.group(2)), records(d, 4)
+    print("\nCLI rmd160 -l both over 2^34 keys: -n 0x1000000 -> %.0f Mkeys/s, -n 0x100000000 -> %.0f Mkeys/s"
+          % (rates["0x1000000"] / 1e6, rates["0x100000000"] / 1e6))
+    assert found["0x1000000"] == found["0x100000000"] and len(found["0x1000000"]) == len(idxs)
+    assert rates["0x1000000"] >= 0.97 * rates["0x100000000"], rates
