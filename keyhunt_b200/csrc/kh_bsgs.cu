@@ -17,9 +17,16 @@
 
 using namespace kh;
 
-#define KH_BLOCK 256
+// CTA shape of the walk kernels of this file (A/B knobs; T is a multiple of 256 whatever the shape, see kh_pick_T)
+#ifndef KH_BSGS_BLOCK
+#define KH_BSGS_BLOCK 256
+#endif
+#define KH_BLOCK KH_BSGS_BLOCK
 #ifndef KH_GIANT_MINBLOCKS
-#define KH_GIANT_MINBLOCKS 2
+#define KH_GIANT_MINBLOCKS (512 / KH_BSGS_BLOCK)
+#endif
+#ifndef KH_BABY_MINBLOCKS
+#define KH_BABY_MINBLOCKS (512 / KH_BSGS_BLOCK)
 #endif
 
 __device__ __forceinline__ void kh_stage_table_b(uint32_t *smem, const uint32_t *gtab) {
@@ -29,7 +36,7 @@ __device__ __forceinline__ void kh_stage_table_b(uint32_t *smem, const uint32_t 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(KH_BLOCK, 2) kh_baby_kernel(WalkParams wp, BsgsTables bt) {
+__global__ void __launch_bounds__(KH_BLOCK, KH_BABY_MINBLOCKS) kh_baby_kernel(WalkParams wp, BsgsTables bt) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table_b(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

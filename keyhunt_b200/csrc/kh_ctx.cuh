@@ -13,6 +13,9 @@
 #include "emit.cuh"
 #include "setup.cuh"
 
+// walker-thread counts are multiples of this, whatever CTA shape a kernel uses (128 or 256 threads)
+#define KH_T_ALIGN 256
+
 struct kh_ctx {
   int device = 0;
   int sm_count = 0;

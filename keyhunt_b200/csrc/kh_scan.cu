@@ -83,9 +83,9 @@ double kh_time_end(kh_ctx *c) {
 
 uint64_t kh_pick_T(kh_ctx *c, uint64_t n_batches) {
   uint64_t tmax = (uint64_t)c->sm_count * (uint64_t)c->threads_per_sm;
-  tmax = (tmax / KH_BLOCK) * KH_BLOCK;
-  if (tmax < KH_BLOCK) tmax = KH_BLOCK;
-  uint64_t need = ((n_batches + KH_BLOCK - 1) / KH_BLOCK) * KH_BLOCK;
+  tmax = (tmax / KH_T_ALIGN) * KH_T_ALIGN;
+  if (tmax < KH_T_ALIGN) tmax = KH_T_ALIGN;
+  uint64_t need = ((n_batches + KH_T_ALIGN - 1) / KH_T_ALIGN) * KH_T_ALIGN;
   return need < tmax ? need : tmax;
 }
 
@@ -411,9 +411,8 @@ int kh_get_table(kh_ctx *c, uint8_t *dst20, uint64_t cap_records, uint64_t *n_re
 
 template <int KIND>
 static cudaError_t launch_scan(kh_ctx *c, const WalkParams &wp, const ScanTargets &tg) {
-  const unsigned blocks = (unsigned)(wp.T / KH_BLOCK);
-  if (c->endomorphism) kh_scan_kernel<KIND, true><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
-  else kh_scan_kernel<KIND, false><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
+  if (c->endomorphism) kh_scan_kernel<KIND, true><<<(unsigned)(wp.T / ScanShape<KIND, true>::BLOCK), ScanShape<KIND, true>::BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
+  else kh_scan_kernel<KIND, false><<<(unsigned)(wp.T / ScanShape<KIND, false>::BLOCK), ScanShape<KIND, false>::BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
   return cudaGetLastError();
 }
 

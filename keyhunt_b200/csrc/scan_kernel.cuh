@@ -10,6 +10,19 @@
 #ifndef KH_SCAN_MINBLOCKS
 #define KH_SCAN_MINBLOCKS (512 / KH_BLOCK)
 #endif
+// the x-only walk has no hash state to keep alive: its CTA shape is a knob of its own (A/B: registers vs resident warps)
+#ifndef KH_XPOINT_BLOCK
+#define KH_XPOINT_BLOCK KH_BLOCK
+#endif
+#ifndef KH_XPOINT_MINBLOCKS
+#define KH_XPOINT_MINBLOCKS (512 / KH_XPOINT_BLOCK)
+#endif
+template <int KIND, bool ENDO>
+struct ScanShape {
+  static constexpr bool XP = (KIND == kh::KH_SCAN_XPOINT) && !ENDO;
+  static constexpr int BLOCK = XP ? KH_XPOINT_BLOCK : KH_BLOCK;
+  static constexpr int MINBLOCKS = XP ? KH_XPOINT_MINBLOCKS : KH_SCAN_MINBLOCKS;
+};
 
 __device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *gtab) {
   const uint4 *src = reinterpret_cast<const uint4 *>(gtab);
@@ -19,7 +32,7 @@ __device__ __forceinline__ void kh_stage_table(uint32_t *smem, const uint32_t *g
 }
 
 template <int KIND, bool ENDO, bool VANITY = false>
-__global__ void __launch_bounds__(KH_BLOCK, KH_SCAN_MINBLOCKS) kh_scan_kernel(kh::WalkParams wp, kh::ScanTargets tg) {
+__global__ void __launch_bounds__((ScanShape<KIND, ENDO>::BLOCK), (ScanShape<KIND, ENDO>::MINBLOCKS)) kh_scan_kernel(kh::WalkParams wp, kh::ScanTargets tg) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
