@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t se
 #pragma unroll
           for (int k = 0; k < 4; k++) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(b[4 * (i - 4) + k]) : "r"(a[i]), "r"(it));
         }
+      } else if (KIND == 7) {
+        // the x-only walk's own mix: per point 224 wide multiply-adds in carry chains and ~470 ALU-pipe ops (ncu), i.e.
+        // 16 IMAD.WIDE.U32.X + 34 ALU ops per trip here (half LOP3, half carry-free IADD3)
+        if (i < 4) kh::kh_mad_row(row[i], a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], row[i][0] | 1u);
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(b[i]) : "r"(a[i]), "r"(it));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(a[i]) : "r"(b[i]), "r"(it));
       } else {
         asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fm), "f"(fa));
       }
@@ -168,9 +174,9 @@ extern "C" int kh_pipe_peak(kh_ctx *c, double out[8]) {
   out[4] = run_pipe<4>(c, d_out, 2);
   out[5] = run_pipe<5>(c, d_out, 2);   // 16 IMAD.WIDE.X + 16 IADD3 per loop trip
   out[6] = run_pipe<6>(c, d_out, 1);
-  out[7] = 0;
+  out[7] = run_pipe<7>(c, d_out, 1);   // trips x 16 per second = IMAD.WIDE.U32.X per second inside the walk's mix (16 per trip)
   cudaFree(d_out);
-  c->stats.other_launches += 28;
+  c->stats.other_launches += 32;
   KH_CUDA(c, cudaGetLastError());
   return KH_OK;
 }

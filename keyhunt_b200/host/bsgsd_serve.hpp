@@ -44,16 +44,30 @@ static bool bsgsd_send(int fd, const std::string &s) {
 struct BsgsdRequest { bool http = false; std::string pubkey, from, to; };
 
 // 1 = parsed, 0 = malformed (caller answers 400), -1 = connection gone (no answer), -2 = too large (HTTP 413)
+// A request must arrive within BSGSD_READ_DEADLINE_S seconds IN TOTAL: the per-recv timeout alone would let a client that
+// trickles one byte every few seconds hold the (one-request-at-a-time) server for weeks.
+#ifndef BSGSD_READ_DEADLINE_S
+#define BSGSD_READ_DEADLINE_S 15
+#endif
+static ssize_t bsgsd_recv(int fd, char *buf, size_t cap, int flags, const std::chrono::steady_clock::time_point &t0) {
+  const double left = BSGSD_READ_DEADLINE_S - std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (left <= 0) return -1;
+  struct timeval tv = {(time_t)left, (suseconds_t)((left - (double)(time_t)left) * 1e6) + 1};
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+  return recv(fd, buf, cap, flags);
+}
+#define recv_deadline(fd, buf, cap, flags) bsgsd_recv(fd, buf, cap, flags, t_start)
 static int bsgsd_read_request(int fd, BsgsdRequest &rq) {
+  const auto t_start = std::chrono::steady_clock::now();
   char buf[1024];
-  ssize_t n = recv(fd, buf, sizeof(buf) - 1, MSG_PEEK);
+  ssize_t n = recv_deadline(fd, buf, sizeof(buf) - 1, MSG_PEEK);
   if (n <= 0) return -1;
   rq.http = (memcmp(buf, "POST", (size_t)std::min<ssize_t>(n, 4)) == 0);
   if (rq.http) {
     std::string req;
     size_t hdr_end;
     do {
-      n = recv(fd, buf, sizeof(buf), 0);
+      n = recv_deadline(fd, buf, sizeof(buf), 0);
       if (n <= 0) return -1;
       req.append(buf, (size_t)n);
       if (req.size() > (1u << 20)) return -2;
@@ -68,7 +82,7 @@ static int bsgsd_read_request(int fd, BsgsdRequest &rq) {
       content_length = strtoull(head.c_str() + p, NULL, 10);
     }
     while (body.size() < content_length) {
-      n = recv(fd, buf, sizeof(buf), 0);
+      n = recv_deadline(fd, buf, sizeof(buf), 0);
       if (n <= 0) return -1;
       body.append(buf, (size_t)n);
       if (body.size() > (1u << 20)) return -2;
@@ -90,7 +104,7 @@ static int bsgsd_read_request(int fd, BsgsdRequest &rq) {
   }
   std::string line;
   do {
-    n = recv(fd, buf, sizeof(buf), 0);
+    n = recv_deadline(fd, buf, sizeof(buf), 0);
     if (n <= 0) return -1;
     line.append(buf, (size_t)n);
     if (line.size() > 4096) return 0;
@@ -122,7 +136,14 @@ static bool bsgsd_parse_pubkey(const std::string &s, uint8_t xy[64], bool &compr
     memcpy(xy, raw + 1, 32); compressed = true;
     return true;
   }
-  if (s.size() == 130 && is_hex(s) && hex2bin(s, raw, 65) && raw[0] == 4) { memcpy(xy, raw + 1, 64); compressed = false; return true; }
+  if (s.size() == 130 && is_hex(s) && hex2bin(s, raw, 65) && raw[0] == 4) {
+    // the point must be on the curve with canonical coordinates (x, y < p, y^2 = x^3 + 7): the y the curve gives for this x and
+    // this parity must be the y that was sent; anything else gets 400 like a malformed compressed key
+    uint8_t y[32];
+    if (!decompress_pub(raw + 1, raw[64] & 1, y) || memcmp(y, raw + 33, 32) != 0) return false;
+    memcpy(xy, raw + 1, 64); compressed = false;
+    return true;
+  }
   return false;
 }
 static bool bsgsd_hex_ok(const std::string &s) { for (char c : s) if (!isxdigit((unsigned char)c)) return false; return s.size() <= 64; }   // isValidHex util.c:347
@@ -140,6 +161,7 @@ static int bsgsd_search(std::vector<kh_ctx *> &gpus, const kh_bsgs_desc &d, cons
   const uint64_t windows = (uint64_t)nw, ng = gpus.size();
   std::vector<int> fnd(ng, 0), err(ng, 0);
   std::vector<U256> keys(ng);
+  std::atomic<bool> stop_all{false};
   auto worker = [&](size_t g) {
     const uint64_t base = windows / ng, rem = windows % ng;
     const uint64_t first = g * base + std::min<uint64_t>(g, rem), cnt = base + (g < rem ? 1 : 0);
@@ -147,7 +169,16 @@ static int bsgsd_search(std::vector<kh_ctx *> &gpus, const kh_bsgs_desc &d, cons
     const U256 f = u_add(from, u_mul_u64(two_n, first));
     U256 t = u_add(f, u_mul_u64(two_n, cnt));
     if (first + cnt == windows) t = to;                                          // the last window keeps the reference's overshoot past `to`
-    if (kh_bsgs_search(gpus[g], xy, f.b, t.b, keys[g].b, &fnd[g]) != KH_OK) { fprintf(stderr, "[E] %s\n", kh_last_error(gpus[g])); err[g] = 1; }
+    // in slices of 2^24 windows (a few seconds of giant steps) so that SIGINT / SIGTERM can end a huge request between slices
+    const uint64_t slice = 1ULL << 24;
+    for (uint64_t done = 0; done < cnt && !fnd[g] && !err[g] && !stop_all.load(); done += slice) {
+      if (bsgsd_stop) { err[g] = 1; break; }
+      const uint64_t c = std::min<uint64_t>(slice, cnt - done);
+      const U256 sf = u_add(f, u_mul_u64(two_n, done));
+      const U256 st = (done + c == cnt) ? t : u_add(sf, u_mul_u64(two_n, c));
+      if (kh_bsgs_search(gpus[g], xy, sf.b, st.b, keys[g].b, &fnd[g]) != KH_OK) { fprintf(stderr, "[E] %s\n", kh_last_error(gpus[g])); err[g] = 1; }
+      if (fnd[g]) stop_all.store(true);                                         // first key found ends the request on every GPU
+    }
   };
   std::vector<std::thread> th;
   for (size_t g = 0; g < ng; g++) th.emplace_back(worker, g);

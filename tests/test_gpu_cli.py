@@ -198,5 +198,12 @@ def test_cli_small_n_keeps_the_gpu_full(dirs, kh):
         rates[nflag], found[nflag] = int(m.group(2)), records(d, 4)
     print("\nCLI rmd160 -l both over 2^34 keys: -n 0x1000000 -> %.0f Mkeys/s, -n 0x100000000 -> %.0f Mkeys/s"
           % (rates["0x1000000"] / 1e6, rates["0x100000000"] / 1e6))
+    try:        # evidence for profiles/ (the GPU box merges gpurun_out/ back)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump({"what": "keyhunt-b200 -m rmd160 -l both, 1024 targets, 2^34 keys, keys/s printed by the CLI itself (context + target upload included)",
+                   "rate_n_0x1000000": rates["0x1000000"], "rate_n_0x100000000": rates["0x100000000"], "records_identical": found["0x1000000"] == found["0x100000000"]},
+                  open(os.path.join(ROOT, "gpurun_out", "cli_small_n.json"), "w"))
+    except OSError:
+        pass
     assert found["0x1000000"] == found["0x100000000"] and len(found["0x1000000"]) == len(idxs)
     assert rates["0x1000000"] >= 0.97 * rates["0x100000000"], rates

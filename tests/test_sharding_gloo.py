@@ -91,3 +91,53 @@ def test_two_rank_scan_equals_single_process():
     assert same and n == len(set(range(n))) and n >= 10
     assert tmax == 11.0            # max over ranks
     assert 0 < n0 < n              # rank 0 alone does not see every hit
+
+
+def _worker_bsgs(rank, world, port, q):
+    """the host logic of bench.py's strong C4 block / the CLI's `-t N` BSGS: contiguous blocks of 2N-key windows per rank,
+    tables built on every rank, found keys gathered — the oracle stands in for the GPU"""
+    sys.path.insert(0, HERE)
+    from _oracle import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = Oracle()
+    n, k = 1 << 20, 1
+    b = o.bsgs_new(n, k, 1)
+    start, n_windows = 0x8000000001, 11
+    win = 2 * n
+    rnd = random.Random(5)
+    keys = [start, start + 5 * win + 12345, start + (n_windows - 1) * win + win - 1, start + 3 * win, start + n_windows * win + 7] + \
+           [start + rnd.randrange(n_windows * win) for _ in range(3)]
+    first, count = sharding.shard_windows(n_windows, world, rank)
+    results = []
+    for key in keys:
+        pub = o.pubkey(key)
+        got = o.bsgs_search(b, pub, start + first * win, start + (first + count) * win)[0] if count else None
+        merged = sharding.gather_hits(dist, [got] if got is not None else [])
+        if rank == 0:
+            whole = o.bsgs_search(b, pub, start, start + n_windows * win)[0]
+            results.append((key, merged, whole))
+    o.bsgs_free(b)
+    if rank == 0:
+        q.put(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bsgs_windows_equal_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_worker_bsgs, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    found = 0
+    for key, merged, whole in results:
+        assert merged == ([whole] if whole is not None else []), hex(key)
+        found += whole is not None
+    assert found >= 6          # every key inside the range is found by exactly one rank; the one past the end by nobody

@@ -20,4 +20,4 @@ for f, h in hist.items():
     if pat and pat not in f: continue
     tot = sum(h.values())
     print(f"== {f}  total {tot}")
-    print("   " + "  ".join(f"{k}:{v}" for k, v in h.most_common(24)))
+    print("   " + "  ".join(f"{k}:{v}" for k, v in h.most_common()))
