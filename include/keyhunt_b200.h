@@ -147,8 +147,9 @@ int kh_int_peak(kh_ctx *ctx, double out_ops_per_s[6]);
  * [0] IMAD.WIDE.U32 without carry chain, [1] IMAD.HI.U32, [2] DFMA (FP64 pipe), [3] DADD, [4] DFMA + IMAD.WIDE issued
  * together (do the FP64 and FMA-heavy pipes overlap?), [5] IMAD.WIDE.U32.X + IADD3 together (multiplier + carry work),
  * [6] FFMA, [7] IMAD.WIDE.U32.X per second when issued in the x-only walk's own mix (16 wide multiply-adds in carry chains per
- * 32 ALU-pipe ops, the ratio ncu measures in kh_scan_kernel<XPOINT>): the practical ceiling of the EC-bound kernels */
-int kh_pipe_peak(kh_ctx *ctx, double out_ops_per_s[8]);
+ * 32 ALU-pipe ops, the ratio ncu measures in kh_scan_kernel<XPOINT>): the practical ceiling of the EC-bound kernels,
+ * [8] IMAD.WIDE.U32 without carry + LOP3 issued together (total ops/s), [9..15] reserved (0) */
+int kh_pipe_peak(kh_ctx *ctx, double out_ops_per_s[16]);
 /* hash micro-benchmarks in isolation: [0] SHA-256 compressions/s, [1] RIPEMD-160 blocks/s, at blocks_per_sm CTAs of 256 */
 int kh_hash_peak(kh_ctx *ctx, int blocks_per_sm, double out_blocks_per_s[2]);
 

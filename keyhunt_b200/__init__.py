@@ -299,9 +299,9 @@ class KeyHunt:
 
     def pipe_peak(self):
         """more measured pipe rates (thread-ops/s, whole chip): the evidence behind the choice of multiplier"""
-        arr = (C.c_double * 8)()
+        arr = (C.c_double * 16)()
         self._ck(self._lib.kh_pipe_peak(self._h, arr))
-        return dict(zip(["imad_wide_nocarry", "imad_hi", "dfma", "dadd", "dfma_plus_imad_wide", "imad_wide_plus_iadd3", "ffma", "imad_wide_in_walk_mix"],
+        return dict(zip(["imad_wide_nocarry", "imad_hi", "dfma", "dadd", "dfma_plus_imad_wide", "imad_wide_plus_iadd3", "ffma", "imad_wide_in_walk_mix", "imad_wide_nocarry_plus_lop3"],
                         [float(x) for x in arr]))
 
     def hash_peak(self, blocks_per_sm=2):

@@ -101,6 +101,7 @@ struct ScanEmit {
 #endif
   static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT || ENDO);
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
+  static constexpr bool WALK_INLOOP = false;   // loop shape of the walk (walk.cuh walk_run)
   const ScanTargets &tg;
   KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
 
@@ -221,6 +222,7 @@ KH_HD bool bsgs_pre_test(const uint32_t *pre, uint32_t k, const fe &x) {
 
 // baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
 struct BabyEmit {
+  static constexpr bool WALK_INLOOP = false;
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
   static constexpr bool PAIRS = true;
@@ -282,6 +284,7 @@ struct GiantParams {
 #define KH_GIANT_OUTLINE 0
 #endif
 struct GiantEmit {
+  static constexpr bool WALK_INLOOP = false;
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = KH_GIANT_OUTLINE != 0;
   static constexpr bool PAIRS = true;

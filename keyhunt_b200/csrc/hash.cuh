@@ -74,10 +74,42 @@ KH_HD uint32_t kh_addf(uint32_t a, uint32_t b) {
 #endif
 }
 
+// KH_SHA_SIGMA_WIDE (A/B knob): rotations as wide multiplies on the FMA-heavy pipe.  x * 2^(32-n) is a 64-bit
+// value whose halves hold the two parts of rotr(x, n) in disjoint bits, so rotr = hi ^ lo and x >> n = hi; the XOR of the
+// halves folds into 3-input LOP3s.  Per function: Sigma 3 SHF + 1 LOP3 -> 3 IMAD.WIDE + 3 LOP3 (-1 ALU op), sigma
+// 3 SHF + 1 LOP3 -> 3 IMAD.WIDE + 2 LOP3 (-2 ALU ops).  1 = the message-schedule sigmas only, 2 = Sigmas as well.
+#ifndef KH_SHA_SIGMA_WIDE
+#define KH_SHA_SIGMA_WIDE 0
+#endif
+#if defined(__CUDA_ARCH__) && KH_SHA_SIGMA_WIDE
+__device__ __forceinline__ void kh_mulw(uint32_t &lo, uint32_t &hi, uint32_t x, uint32_t m) {
+  asm("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(x), "r"(m));
+}
+__device__ __forceinline__ uint32_t kh_sig3w(uint32_t x, int r1, int r2, int r3) {      // rotr r1 ^ rotr r2 ^ rotr r3
+  uint32_t l1, h1, l2, h2, l3, h3;
+  kh_mulw(l1, h1, x, 1u << (32 - r1)); kh_mulw(l2, h2, x, 1u << (32 - r2)); kh_mulw(l3, h3, x, 1u << (32 - r3));
+  return (l1 ^ h1 ^ l2) ^ (h2 ^ l3 ^ h3);
+}
+__device__ __forceinline__ uint32_t kh_sig2sw(uint32_t x, int r1, int r2, int s) {      // rotr r1 ^ rotr r2 ^ (x >> s)
+  uint32_t l1, h1, l2, h2, l3, h3;
+  kh_mulw(l1, h1, x, 1u << (32 - r1)); kh_mulw(l2, h2, x, 1u << (32 - r2)); kh_mulw(l3, h3, x, 1u << (32 - s));
+  return (l1 ^ h1 ^ l2) ^ (h2 ^ h3);
+}
+#define KH_SHA_s0(x) kh_sig2sw(x, 7, 18, 3)
+#define KH_SHA_s1(x) kh_sig2sw(x, 17, 19, 10)
+#if KH_SHA_SIGMA_WIDE >= 2
+#define KH_SHA_S0(x) kh_sig3w(x, 2, 13, 22)
+#define KH_SHA_S1(x) kh_sig3w(x, 6, 11, 25)
+#else
+#define KH_SHA_S0(x) (rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22))
+#define KH_SHA_S1(x) (rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25))
+#endif
+#else
 #define KH_SHA_S0(x) (rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22))
 #define KH_SHA_S1(x) (rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25))
 #define KH_SHA_s0(x) (rotr32(x, 7) ^ rotr32(x, 18) ^ ((x) >> 3))
 #define KH_SHA_s1(x) (rotr32(x, 17) ^ rotr32(x, 19) ^ ((x) >> 10))
+#endif
 #define KH_SHA_CH(x, y, z) (((x) & (y)) ^ (~(x) & (z)))
 #define KH_SHA_MAJ(x, y, z) (((x) & (y)) ^ ((x) & (z)) ^ ((y) & (z)))
 #define KH_SHA_RND(a, b, c, d, e, f, g, h, k, wv)                                   \

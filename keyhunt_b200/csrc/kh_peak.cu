@@ -91,8 +91,10 @@ __global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t se
   uint32_t a[PEAK_CHAINS], b[PEAK_CHAINS];
   double d[PEAK_CHAINS];
   float f[PEAK_CHAINS];
+  uint32_t f_as_u[PEAK_CHAINS];
 #pragma unroll
   for (int i = 0; i < PEAK_CHAINS; i++) {
+    f_as_u[i] = seed * 3u + i;
     a[i] = seed + threadIdx.x * 977u + i; b[i] = (seed * 31u + blockIdx.x + i * 7u) | 1u;
     w[i] = ((uint64_t)a[i] << 32) | b[i];
     d[i] = 1.0 + 1e-9 * (double)(a[i] & 1023u);
@@ -126,6 +128,9 @@ __global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t se
 #pragma unroll
           for (int k = 0; k < 4; k++) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(b[4 * (i - 4) + k]) : "r"(a[i]), "r"(it));
         }
+      } else if (KIND == 8) {   // IMAD.WIDE.U32 without carries + LOP3: do the FMA-heavy and the ALU pipe overlap when no carry is involved?
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(f_as_u[i]) : "r"(b[i]), "r"(it));
       } else if (KIND == 7) {
         // the x-only walk's own mix: per point 224 wide multiply-adds in carry chains and ~470 ALU-pipe ops (ncu), i.e.
         // 16 IMAD.WIDE.U32.X + 34 ALU ops per trip here (half LOP3, half carry-free IADD3)
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t se
   }
   uint32_t r = 0;
 #pragma unroll
-  for (int i = 0; i < PEAK_CHAINS; i++) r ^= a[i] ^ b[i] ^ (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32) ^ (uint32_t)__double2loint(d[i]) ^ __float_as_uint(f[i]);
+  for (int i = 0; i < PEAK_CHAINS; i++) r ^= a[i] ^ b[i] ^ (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32) ^ (uint32_t)__double2loint(d[i]) ^ __float_as_uint(f[i]) ^ f_as_u[i];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -162,7 +167,7 @@ static double run_pipe(kh_ctx *c, uint32_t *d_out, int ops_per_step) {
   return best;
 }
 
-extern "C" int kh_pipe_peak(kh_ctx *c, double out[8]) {
+extern "C" int kh_pipe_peak(kh_ctx *c, double out[16]) {
   if (!c || !out) return KH_EINVAL;
   cudaSetDevice(c->device);
   uint32_t *d_out = nullptr;
@@ -174,9 +179,11 @@ extern "C" int kh_pipe_peak(kh_ctx *c, double out[8]) {
   out[4] = run_pipe<4>(c, d_out, 2);
   out[5] = run_pipe<5>(c, d_out, 2);   // 16 IMAD.WIDE.X + 16 IADD3 per loop trip
   out[6] = run_pipe<6>(c, d_out, 1);
-  out[7] = run_pipe<7>(c, d_out, 1);   // trips x 16 per second = IMAD.WIDE.U32.X per second inside the walk's mix (16 per trip)
+  out[7] = run_pipe<7>(c, d_out, 1);
+  out[8] = run_pipe<8>(c, d_out, 2);   // IMAD.WIDE.U32 (no carry) + LOP3 together, total ops/s
+  for (int i = 9; i < 16; i++) out[i] = 0;   // trips x 16 per second = IMAD.WIDE.U32.X per second inside the walk's mix (16 per trip)
   cudaFree(d_out);
-  c->stats.other_launches += 32;
+  c->stats.other_launches += 36;
   KH_CUDA(c, cudaGetLastError());
   return KH_OK;
 }

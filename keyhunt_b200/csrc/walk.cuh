@@ -100,6 +100,24 @@ KH_HD void walk_flag_inc(uint32_t *p) {
   (*p)++;
 #endif
 }
+// Cold helper (by value: its operands must not become address-taken locals of the walk): the batch product WITHOUT the hop
+// entry, prefix products rewritten accordingly.  Only called when the shared product was zero because the centre is +-W.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+fe walk_cold_product(const uint32_t *tab, kh_u4 *scratch, uint64_t T, uint64_t t, fe px) {
+  fe acc;
+  fe_set_u32(acc, 1);
+#pragma unroll 1
+  for (int e = 0; e < KH_TAB_ENTRIES; e++) {
+    if (e > 0) { fe gx, dx; tab_load_x(gx, tab, e); fe_sub(dx, gx, px); fe_mul_cold(acc, acc, dx); }
+    if (e < KH_TAB_ENTRIES - 1) scratch_store(scratch, T, t, e, acc);
+  }
+  return acc;
+}
+
 // Walks `steps` batches for walker thread t.  `tab` is the table in shared memory (device) or plain
 // memory (host test build).  For each point calls emit.point(x, y, batch, idx) where key index in the
 // range is batch*1024 + idx; y is valid only if Emit::NEED_Y.
@@ -137,6 +155,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
     if (fe_is_zero(acc)) {                           // cold
       fe gx0;
       tab_load_x(gx0, tab, 0);
+#ifndef KH_X_NOREDO
       if (fe_eq(gx0, px)) {                          // the hop entry alone may be the culprit: batch product without it
         fe_set_u32(acc, 1);
 #pragma unroll 1
@@ -145,10 +164,12 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
           if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
         }
       }
+#endif
       if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
     }
     fe inv;
-    fe_inv_reg(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0
+    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0.  (By reference on purpose: inv then lives in
+                        // local memory across the hot loop, one load/store per pair of points, and frees eight registers for the hash state.)
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1
@@ -209,6 +230,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       tab_load(gx, gy, tab, 0);
       fe_sub(dx, gx, px);
       fe_sub(dy, gy, py);
+#ifndef KH_X_NOCOLDMOVE
       if (fe_is_zero(inv) || fe_is_zero(dx)) {        // cold: collapsed batch, or the centre is +-W
         if (fe_is_zero(dx)) {
           if (!fe_is_zero(dy)) { walk_flag_or(wp.flags, 1u); break; }      // C = -W: the next centre is the point at infinity
@@ -217,6 +239,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
         }
         fe_inv_reg(inv, dx);
       }
+#endif
       fe_mul_cold(s, dy, inv);
       fe_mul_cold(s2, s, s);
       fe_sub(x3, s2, px);
@@ -227,6 +250,137 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
   }
 #pragma unroll
   for (int l = 0; l < 8; l++) { wp.centers[(uint64_t)l * wp.T + t] = px.v[l]; wp.centers[(uint64_t)(8 + l) * wp.T + t] = py.v[l]; }
+}
+
+// r1 loop shape (the centre, its move and the cold cases inside the backward loop): A/B against the peeled form above
+template <class Emit>
+KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
+  constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
+  fe px, py;
+#pragma unroll
+  for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
+
+#pragma unroll 1
+  for (uint32_t step = 0; step < wp.steps; step++) {
+    const uint64_t batch = wp.batch_base + (uint64_t)step * wp.T + t;
+    if (batch >= wp.n_batches) break;
+
+    // ---- forward pass: prefix products of dx_e = tab[e].x - px ------------------------------------
+    fe acc;
+#pragma unroll 1
+    for (int e = 0; e < KH_TAB_ENTRIES; e++) {
+      fe gx, dx;
+      tab_load_x(gx, tab, e);
+      fe_sub(dx, gx, px);
+      if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
+      if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
+    }
+#ifndef KH_X_NOFWD
+    if (fe_is_zero(acc)) {                           // cold (see the comment above walk_batches)
+      fe gx0;
+      tab_load_x(gx0, tab, 0);
+      if (fe_eq(gx0, px)) acc = walk_cold_product(tab, wp.scratch, wp.T, t, px);   // the hop entry alone may be the culprit
+      if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
+    }
+#endif
+    fe inv;
+    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0
+
+    // ---- backward pass: peel the inverses off and produce the points ------------------------------
+#pragma unroll 1
+    for (int e = KH_TAB_ENTRIES - 1; e >= 0; e--) {
+      fe gx, gy, dinv;
+      bool tangent = false;
+      tab_load(gx, gy, tab, e);
+      if (e > 0) {
+        fe pre, dx;
+        scratch_load(pre, wp.scratch, wp.T, t, e - 1);
+        fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
+        fe_sub(dx, gx, px);
+        fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
+      } else {
+        dinv = inv;                           // what is left of the batch inverse is 1/dx_0 ...
+#ifndef KH_X_NOE0
+        // ... unless the batch had no inverse (0), or the hop was left out of it (exactly 1: the product then started from 1).
+        // No state is carried through the hot loop for this: a genuine 1/dx_0 = 1 just takes the cold path to the same value.
+        if (((dinv.v[0] & ~1u) | dinv.v[1] | dinv.v[2] | dinv.v[3] | dinv.v[4] | dinv.v[5] | dinv.v[6] | dinv.v[7]) == 0) {   // cold
+          fe d0;
+          fe_sub(d0, gx, px);
+          if (fe_is_zero(d0)) {
+            if (!fe_eq(gy, py)) { walk_flag_or(wp.flags, 1u); step = wp.steps - 1; }   // C = -W: the next centre is the point at infinity
+            tangent = true;                         // C = W: slope 3x^2 / 2y through the same formulas (gx = px, gy = py)
+            fe_add(d0, py, py);
+          }
+          fe_inv_reg(dinv, d0);
+        }
+#endif
+      }
+      if (Emit::PAIRS && e != 0 && e != KH_HALF) {
+        // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
+        // emitter, the bloom probes of both points in flight at the same time (memory-level parallelism)
+        fe dyp, dym, sp, sm, xp, xm, c;
+        fe_sub(dyp, gy, py);
+        fe_add(dym, gy, py);
+        fe_mul_sel<OL>(sp, dyp, dinv);
+        fe_mul_sel<OL>(sm, dym, dinv);
+        if (OL) { fe_mul_sel<true>(xp, sp, sp); fe_mul_sel<true>(xm, sm, sm); } else { fe_sqr(xp, sp); fe_sqr(xm, sm); }
+        fe_add(c, px, gx);
+        fe_sub(xp, xp, c);
+        fe_sub(xm, xm, c);
+        emit.pair(xp, (uint32_t)(KH_HALF + e), xm, (uint32_t)(KH_HALF - e), batch);
+        continue;
+      }
+#pragma unroll 1
+      for (int sgn = 0; sgn < 2; sgn++) {
+        if (e == KH_HALF && sgn == 0) continue;        // +512*S belongs to the next batch (pts[0] there)
+        fe x3, y3;
+        uint32_t idx;
+        bool do_emit = true;
+        if (e == 0 && sgn == 0) {                       // the centre itself
+          x3 = px; y3 = py; idx = KH_HALF;
+        } else {
+          fe s, dy, s2;
+          if (tangent) { fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2); }   // cold: only ever at e == 0
+          else if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
+          else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
+          fe_mul_sel<OL>(s, dy, dinv);
+          if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
+          fe_sub(x3, s2, px);
+          fe_sub(x3, x3, gx);
+          if (e == 0) {                                 // new centre: always needs y
+            fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
+            px = x3; py = y3;
+            do_emit = false;
+            idx = 0;
+          } else {
+            if (Emit::NEED_Y) {
+              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
+              else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
+            } else {
+              y3 = py;
+            }
+            idx = (sgn == 0) ? (uint32_t)(KH_HALF + e) : (uint32_t)(KH_HALF - e);
+          }
+        }
+        if (do_emit) emit.point(x3, y3, batch, idx);
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 8; l++) { wp.centers[(uint64_t)l * wp.T + t] = px.v[l]; wp.centers[(uint64_t)(8 + l) * wp.T + t] = py.v[l]; }
+}
+
+
+// Which loop shape a kernel uses is a property of its emitter (Emit::WALK_INLOOP): both are the same arithmetic; ptxas
+// allocates registers differently around them and the hash-heavy kernels are sensitive to that (A/B in DESIGN.md §4).
+// -DKH_WALK_SHAPE=0 / 1 forces the peeled / in-loop form everywhere (A/B builds).
+template <class Emit>
+KH_HD void walk_run(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
+#if defined(KH_WALK_SHAPE)
+  if (KH_WALK_SHAPE) walk_batches_inloop(wp, tab, t, emit); else walk_batches(wp, tab, t, emit);
+#else
+  if (Emit::WALK_INLOOP) walk_batches_inloop(wp, tab, t, emit); else walk_batches(wp, tab, t, emit);
+#endif
 }
 
 }  // namespace kh
