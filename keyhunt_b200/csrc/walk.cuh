@@ -76,6 +76,29 @@ KH_HD void scratch_store(kh_u4 *s, uint64_t T, uint64_t t, int e, const fe &a) {
   s[(uint64_t)(2 * e + 1) * T + t] = hi;
 #endif
 }
+// KH_SCRATCH_PREFETCH = D > 0 (A/B knob): at the top of backward iteration e, prefetch the prefix product that iteration
+// e - D will load (a line of the [entry][thread] scratch array), so that its HBM latency is not exposed to the first
+// multiplication of that iteration (ncu: long_scoreboard 1.2 warps per issue cycle in the x-only walk).
+#ifndef KH_SCRATCH_PREFETCH
+#define KH_SCRATCH_PREFETCH 0
+#endif
+KH_HD void scratch_prefetch(const kh_u4 *s, uint64_t T, uint64_t t, int e) {
+#if defined(__CUDA_ARCH__) && KH_SCRATCH_PREFETCH
+  if (e >= 0) {
+    const uint4 *p0 = reinterpret_cast<const uint4 *>(s) + (uint64_t)(2 * e) * T + t;
+    const uint4 *p1 = reinterpret_cast<const uint4 *>(s) + (uint64_t)(2 * e + 1) * T + t;
+#if defined(KH_SCRATCH_PREFETCH_L2)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1));
+#endif
+  }
+#else
+  (void)s; (void)T; (void)t; (void)e;
+#endif
+}
 KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
 #if defined(__CUDA_ARCH__)
   uint4 lo = reinterpret_cast<const uint4 *>(s)[(uint64_t)(2 * e) * T + t];
@@ -116,6 +139,35 @@ fe walk_cold_product(const uint32_t *tab, kh_u4 *scratch, uint64_t T, uint64_t t
     if (e < KH_TAB_ENTRIES - 1) scratch_store(scratch, T, t, e, acc);
   }
   return acc;
+}
+
+// Cold helper (by value, see above): the centre move C + W with an inverse of its own — the tangent when C = W.  The new
+// centre goes to the walker's slot of the centres array in global memory (the hot loop picks it up there, so nothing has to
+// stay in registers across the batch).  Returns false when C = -W: the next centre would be the point at infinity.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+bool walk_cold_move(const uint32_t *tab, uint32_t *centers, uint64_t T, uint64_t t, fe px, fe py) {
+  fe gx, gy, dx, dy, inv, s, s2, x3, y3;
+  tab_load(gx, gy, tab, 0);
+  fe_sub(dx, gx, px);
+  fe_sub(dy, gy, py);
+  if (fe_is_zero(dx)) {
+    if (!fe_is_zero(dy)) return false;
+    fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2);     // slope 3x^2 / 2y
+    fe_add(dx, py, py);
+  }
+  fe_inv(inv, dx);
+  fe_mul_cold(s, dy, inv);
+  fe_mul_cold(s2, s, s);
+  fe_sub(x3, s2, px);
+  fe_sub(x3, x3, gx);
+  fe_sub(y3, gx, x3); fe_mul_cold(y3, y3, s); fe_sub(y3, y3, gy);
+#pragma unroll
+  for (int l = 0; l < 8; l++) { centers[(uint64_t)l * T + t] = x3.v[l]; centers[(uint64_t)(8 + l) * T + t] = y3.v[l]; }
+  return true;
 }
 
 // Walks `steps` batches for walker thread t.  `tab` is the table in shared memory (device) or plain
@@ -179,6 +231,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
+        scratch_prefetch(wp.scratch, wp.T, t, e - 1 - KH_SCRATCH_PREFETCH);
         fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
         fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
@@ -281,6 +334,8 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
       tab_load_x(gx0, tab, 0);
       if (fe_eq(gx0, px)) acc = walk_cold_product(tab, wp.scratch, wp.T, t, px);   // the hop entry alone may be the culprit
       if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
+      // the centre move cannot ride in this batch: done here, parked in the centres array (picked up at e == 0 below)
+      if (!walk_cold_move(tab, wp.centers, wp.T, t, px, py)) { walk_flag_or(wp.flags, 1u); break; }
     }
 #endif
     fe inv;
@@ -290,30 +345,16 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
 #pragma unroll 1
     for (int e = KH_TAB_ENTRIES - 1; e >= 0; e--) {
       fe gx, gy, dinv;
-      bool tangent = false;
       tab_load(gx, gy, tab, e);
       if (e > 0) {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
+        scratch_prefetch(wp.scratch, wp.T, t, e - 1 - KH_SCRATCH_PREFETCH);
         fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
         fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
       } else {
-        dinv = inv;                           // what is left of the batch inverse is 1/dx_0 ...
-#ifndef KH_X_NOE0
-        // ... unless the batch had no inverse (0), or the hop was left out of it (exactly 1: the product then started from 1).
-        // No state is carried through the hot loop for this: a genuine 1/dx_0 = 1 just takes the cold path to the same value.
-        if (((dinv.v[0] & ~1u) | dinv.v[1] | dinv.v[2] | dinv.v[3] | dinv.v[4] | dinv.v[5] | dinv.v[6] | dinv.v[7]) == 0) {   // cold
-          fe d0;
-          fe_sub(d0, gx, px);
-          if (fe_is_zero(d0)) {
-            if (!fe_eq(gy, py)) { walk_flag_or(wp.flags, 1u); step = wp.steps - 1; }   // C = -W: the next centre is the point at infinity
-            tangent = true;                         // C = W: slope 3x^2 / 2y through the same formulas (gx = px, gy = py)
-            fe_add(d0, py, py);
-          }
-          fe_inv_reg(dinv, d0);
-        }
-#endif
+        dinv = inv;                           // what is left of the batch inverse is 1/dx_0 (cold exceptions: see e == 0 below)
       }
       if (Emit::PAIRS && e != 0 && e != KH_HALF) {
         // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
@@ -340,8 +381,7 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
           x3 = px; y3 = py; idx = KH_HALF;
         } else {
           fe s, dy, s2;
-          if (tangent) { fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2); }   // cold: only ever at e == 0
-          else if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
+          if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
           fe_mul_sel<OL>(s, dy, dinv);
           if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
@@ -349,6 +389,19 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
             fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
+#ifndef KH_X_NOE0
+            // Cold: what was left of the batch inverse is 0 if the batch had none and exactly 1 if the hop was left out of it
+            // (the product then started from 1).  The centre move was then done before the batch and parked in the centres
+            // array.  No state is carried through the hot loop for this; a genuine 1/dx_0 = 1 fails the second test.
+            if (((dinv.v[0] & ~1u) | dinv.v[1] | dinv.v[2] | dinv.v[3] | dinv.v[4] | dinv.v[5] | dinv.v[6] | dinv.v[7]) == 0) {
+              fe d0;
+              fe_sub(d0, gx, px);
+              if (fe_is_zero(dinv) || fe_is_zero(d0)) {
+#pragma unroll
+                for (int l = 0; l < 8; l++) { x3.v[l] = wp.centers[(uint64_t)l * wp.T + t]; y3.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
+              }
+            }
+#endif
             px = x3; py = y3;
             do_emit = false;
             idx = 0;
