@@ -101,7 +101,6 @@ struct ScanEmit {
 #endif
   static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT || ENDO);
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
-  static constexpr bool WALK_INLOOP = false;   // loop shape of the walk (walk.cuh walk_run)
   const ScanTargets &tg;
   KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
 
@@ -214,15 +213,47 @@ struct BsgsTables {
   uint32_t pre_k;
   uint32_t pad;
 };
+// One random 4-byte read of the baby-point prefix bitmap (64 GB at -k 512) per giant step.  ncu (profiles/r02_giant_*): L1 asks
+// L2 for ONE 32-byte sector per probe, but L2 looks up and fetches all FOUR sectors of the 128-byte line from DRAM
+// (lts__t_sectors_srcunit_tex_op_read = 4 x lts__t_requests; dram__sectors_read = the same) — the 145 B per giant step are L2
+// sector promotion, not page-table reads.  KH_PRE_LD selects the load flavour (A/B):
+//   0 = ld.global.nc (LDG.CONSTANT)   1 = ld.global.nc.L2::64B   2 = ld.global.L2::64B   3 = ld.global.cv
+//   4 = ld.global.cg                  5 = atom.global.or.b32 with 0 (L2 atomic unit works on 32-byte sectors)
+//   6 = ld.global.nc.L1::no_allocate.L2::64B
+#ifndef KH_PRE_LD
+#define KH_PRE_LD 0
+#endif
+KH_HD uint32_t kh_ld_probe32(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+#if KH_PRE_LD == 0
+  v = __ldg(p);
+#elif KH_PRE_LD == 1
+  asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#elif KH_PRE_LD == 2
+  asm volatile("ld.global.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#elif KH_PRE_LD == 3
+  asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#elif KH_PRE_LD == 4
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#elif KH_PRE_LD == 5
+  asm volatile("atom.global.or.b32 %0, [%1], 0;" : "=r"(v) : "l"(p) : "memory");
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
+  return v;
+#else
+  return *p;
+#endif
+}
 KH_HD uint64_t bsgs_pre_index(const fe &x, uint32_t k) { return (((uint64_t)x.v[7] << 32) | x.v[6]) >> (64 - k); }
 KH_HD bool bsgs_pre_test(const uint32_t *pre, uint32_t k, const fe &x) {
   const uint64_t idx = bsgs_pre_index(x, k);
-  return (kh_ld_u32(pre + (idx >> 5)) >> (uint32_t)(idx & 31)) & 1u;
+  return (kh_ld_probe32(pre + (idx >> 5)) >> (uint32_t)(idx & 31)) & 1u;
 }
 
 // baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
 struct BabyEmit {
-  static constexpr bool WALK_INLOOP = false;
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
   static constexpr bool PAIRS = true;
@@ -284,7 +315,6 @@ struct GiantParams {
 #define KH_GIANT_OUTLINE 0
 #endif
 struct GiantEmit {
-  static constexpr bool WALK_INLOOP = false;
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = KH_GIANT_OUTLINE != 0;
   static constexpr bool PAIRS = true;

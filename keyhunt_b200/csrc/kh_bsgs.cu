@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(KH_BLOCK, KH_BABY_MINBLOCKS) kh_baby_kernel(Wa
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wp.T) return;
   BabyEmit emit(bt);
-  walk_run(wp, kh_smem_tab, t, emit);
+  walk_batches(wp, kh_smem_tab, t, emit);
 }
 
 __global__ void __launch_bounds__(KH_BLOCK, KH_GIANT_MINBLOCKS) kh_giant_kernel(WalkParams wp, GiantParams gp) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(KH_BLOCK, KH_GIANT_MINBLOCKS) kh_giant_kernel(
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wp.T) return;
   GiantEmit emit(gp);
-  walk_run(wp, kh_smem_tab, t, emit);
+  walk_batches(wp, kh_smem_tab, t, emit);
 }
 
 // ---- bP table sort -----------------------------------------------------------------------------------

@@ -91,14 +91,15 @@ uint64_t kh_pick_T(kh_ctx *c, uint64_t n_batches) {
 
 int kh_ensure_walk_buffers(kh_ctx *c, uint64_t T) {
   if (!c->d_gtab) KH_CUDA(c, cudaMalloc(&c->d_gtab, KH_TAB_WORDS * sizeof(uint32_t)));
-  if (!c->d_flags) {
-    KH_CUDA(c, cudaMalloc(&c->d_flags, 16 * sizeof(uint32_t)));
-    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(uint32_t), c->stream));
-  }
   if (T > c->T_alloc) {
     if (c->d_centers) cudaFree(c->d_centers);
     if (c->d_scratch) cudaFree(c->d_scratch);
-    c->d_centers = nullptr; c->d_scratch = nullptr; c->T_alloc = 0;
+    if (c->d_flags) cudaFree(c->d_flags);
+    c->d_centers = nullptr; c->d_scratch = nullptr; c->d_flags = nullptr; c->T_alloc = 0;
+    // walk flags: KH_WALK_FLAG_WORDS counters + one "centre parked" mark per walker (walk.cuh)
+    const size_t flag_words = KH_WALK_FLAG_WORDS + (T + 31) / 32;
+    KH_CUDA(c, cudaMalloc(&c->d_flags, flag_words * sizeof(uint32_t)));
+    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, flag_words * sizeof(uint32_t), c->stream));
     KH_CUDA(c, cudaMalloc(&c->d_centers, 16 * T * sizeof(uint32_t)));
     KH_CUDA(c, cudaMalloc(&c->d_scratch, (size_t)1024 * T * sizeof(kh_u4)));
     c->T_alloc = T;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__((ScanShape<KIND, ENDO>::BLOCK), (ScanShape<KIN
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wp.T) return;
   kh::ScanEmit<KIND, ENDO, VANITY> emit(tg);
-  kh::walk_run(wp, kh_smem_tab, t, emit);
+  kh::walk_batches(wp, kh_smem_tab, t, emit);
 }
 
 // kh_vanity.cu: launches kh_scan_kernel<KIND, endo, true> for KIND = COMP / UNCOMP / BOTH

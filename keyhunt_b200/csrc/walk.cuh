@@ -42,8 +42,10 @@ struct WalkParams {
   uint64_t n_batches;     // batches in the whole range; batch b is processed iff b < n_batches
   uint32_t steps;         // steps of this launch
   uint32_t pad;
-  uint32_t *flags;        // [0] bit 0: a walker reached the point at infinity; [1]: batches that collapsed (see walk_batches)
+  uint32_t *flags;        // [0] bit 0: a walker reached the point at infinity; [1]: batches whose shared inverse did not exist;
+                          // [KH_WALK_FLAG_WORDS + t/32] bit t%32: walker t has a centre parked in `centers` (see walk_batches)
 };
+#define KH_WALK_FLAG_WORDS 16
 
 KH_HD void tab_load(fe &gx, fe &gy, const uint32_t *tab, int e) {
   const uint32_t *p = tab + 16 * e;
@@ -123,6 +125,14 @@ KH_HD void walk_flag_inc(uint32_t *p) {
   (*p)++;
 #endif
 }
+KH_HD void walk_flag_and(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  atomicAnd(p, v);
+#else
+  *p &= v;
+#endif
+}
+
 // Cold helper (by value: its operands must not become address-taken locals of the walk): the batch product WITHOUT the hop
 // entry, prefix products rewritten accordingly.  Only called when the shared product was zero because the centre is +-W.
 #if defined(__CUDACC__)
@@ -142,8 +152,8 @@ fe walk_cold_product(const uint32_t *tab, kh_u4 *scratch, uint64_t T, uint64_t t
 }
 
 // Cold helper (by value, see above): the centre move C + W with an inverse of its own — the tangent when C = W.  The new
-// centre goes to the walker's slot of the centres array in global memory (the hot loop picks it up there, so nothing has to
-// stay in registers across the batch).  Returns false when C = -W: the next centre would be the point at infinity.
+// centre is parked in the walker's slot of the centres array in global memory, so that nothing has to stay in registers
+// across the batch.  Returns false when C = -W: the next centre would be the point at infinity.
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
@@ -179,9 +189,12 @@ bool walk_cold_move(const uint32_t *tab, uint32_t *centers, uint64_t T, uint64_t
 // is +-e*S (a range touching key 0 mod n); the centre itself (pts[512]) is still right in both.  Two
 // things the reference does not have and that therefore must not go wrong here:
 //   * the hop entry: a centre equal to W (`-r 200:...` puts walker T-1 there) would zero the product although the
-//     reference's batch is fine -> the forward pass is redone without entry 0 (cold);
-//   * the centre move: it must never be computed from a zero or missing inverse -> it gets an inverse of its own, or the
-//     tangent when C = W, and raises flags[0] when C = -W (point at infinity) (cold).
+//     reference's batch is fine -> the batch product is redone without entry 0;
+//   * the centre move: it must never come out of a zero or missing inverse -> it is done with an inverse of its own (the
+//     tangent when C = W) and parked in the centres array; C = -W (the next centre is the point at infinity) raises flags[0].
+// All of that happens BEFORE the batch, in out-of-line helpers, when the batch product turns out to be zero, plus one
+// state-free test AFTER the batch; the hot loop itself is untouched (an in-loop test cost the C2 kernel 3 %, moving the centre
+// out of the loop 4.6 %: the hash kernels sit at the 128-register cap and ptxas allocates differently around any change).
 template <class Emit>
 KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
   constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
@@ -204,142 +217,18 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
-    if (fe_is_zero(acc)) {                           // cold
-      fe gx0;
-      tab_load_x(gx0, tab, 0);
-#ifndef KH_X_NOREDO
-      if (fe_eq(gx0, px)) {                          // the hop entry alone may be the culprit: batch product without it
-        fe_set_u32(acc, 1);
-#pragma unroll 1
-        for (int e = 0; e < KH_TAB_ENTRIES; e++) {
-          if (e > 0) { fe gx, dx; tab_load_x(gx, tab, e); fe_sub(dx, gx, px); fe_mul_cold(acc, acc, dx); }
-          if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
-        }
-      }
-#endif
-      if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
-    }
-    fe inv;
-    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0.  (By reference on purpose: inv then lives in
-                        // local memory across the hot loop, one load/store per pair of points, and frees eight registers for the hash state.)
-
-    // ---- backward pass: peel the inverses off and produce the points ------------------------------
-#pragma unroll 1
-    for (int e = KH_TAB_ENTRIES - 1; e >= 1; e--) {
-      fe gx, gy, dinv;
-      tab_load(gx, gy, tab, e);
-      {
-        fe pre, dx;
-        scratch_load(pre, wp.scratch, wp.T, t, e - 1);
-        scratch_prefetch(wp.scratch, wp.T, t, e - 1 - KH_SCRATCH_PREFETCH);
-        fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
-        fe_sub(dx, gx, px);
-        fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
-      }
-      if (Emit::PAIRS && e != KH_HALF) {
-        // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
-        // emitter, the bloom probes of both points in flight at the same time (memory-level parallelism)
-        fe dyp, dym, sp, sm, xp, xm, c;
-        fe_sub(dyp, gy, py);
-        fe_add(dym, gy, py);
-        fe_mul_sel<OL>(sp, dyp, dinv);
-        fe_mul_sel<OL>(sm, dym, dinv);
-        if (OL) { fe_mul_sel<true>(xp, sp, sp); fe_mul_sel<true>(xm, sm, sm); } else { fe_sqr(xp, sp); fe_sqr(xm, sm); }
-        fe_add(c, px, gx);
-        fe_sub(xp, xp, c);
-        fe_sub(xm, xm, c);
-        emit.pair(xp, (uint32_t)(KH_HALF + e), xm, (uint32_t)(KH_HALF - e), batch);
-        continue;
-      }
-#pragma unroll 1
-      for (int sgn = 0; sgn < 2; sgn++) {
-        fe x3, y3;
-        uint32_t idx;
-        if (e == KH_HALF && sgn == 0) {                 // +512*S belongs to the next batch (pts[0] there): this slot
-          x3 = px; y3 = py; idx = KH_HALF;              // carries the centre itself instead
-        } else {
-          fe s, dy, s2;
-          if (sgn == 0) fe_sub(dy, gy, py);             // C + e*S
-          else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
-          fe_mul_sel<OL>(s, dy, dinv);
-          if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
-          fe_sub(x3, s2, px);
-          fe_sub(x3, x3, gx);
-          if (Emit::NEED_Y) {
-            if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
-            else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
-          } else {
-            y3 = py;
-          }
-          idx = (sgn == 0) ? (uint32_t)(KH_HALF + e) : (uint32_t)(KH_HALF - e);
-        }
-        emit.point(x3, y3, batch, idx);
-      }
-    }
-
-    // ---- centre move C + W: what is left of inv is 1/dx_0 (once per batch: the shared out-of-line multiplier) ------
-    {
-      fe gx, gy, dx, dy, s, s2, x3, y3;
-      tab_load(gx, gy, tab, 0);
-      fe_sub(dx, gx, px);
-      fe_sub(dy, gy, py);
-#ifndef KH_X_NOCOLDMOVE
-      if (fe_is_zero(inv) || fe_is_zero(dx)) {        // cold: collapsed batch, or the centre is +-W
-        if (fe_is_zero(dx)) {
-          if (!fe_is_zero(dy)) { walk_flag_or(wp.flags, 1u); break; }      // C = -W: the next centre is the point at infinity
-          fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2);   // C = W: tangent, slope 3x^2 / 2y
-          fe_add(dx, py, py);
-        }
-        fe_inv_reg(inv, dx);
-      }
-#endif
-      fe_mul_cold(s, dy, inv);
-      fe_mul_cold(s2, s, s);
-      fe_sub(x3, s2, px);
-      fe_sub(x3, x3, gx);
-      fe_sub(y3, gx, x3); fe_mul_cold(y3, y3, s); fe_sub(y3, y3, gy);
-      px = x3; py = y3;
-    }
-  }
-#pragma unroll
-  for (int l = 0; l < 8; l++) { wp.centers[(uint64_t)l * wp.T + t] = px.v[l]; wp.centers[(uint64_t)(8 + l) * wp.T + t] = py.v[l]; }
-}
-
-// r1 loop shape (the centre, its move and the cold cases inside the backward loop): A/B against the peeled form above
-template <class Emit>
-KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
-  constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
-  fe px, py;
-#pragma unroll
-  for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
-
-#pragma unroll 1
-  for (uint32_t step = 0; step < wp.steps; step++) {
-    const uint64_t batch = wp.batch_base + (uint64_t)step * wp.T + t;
-    if (batch >= wp.n_batches) break;
-
-    // ---- forward pass: prefix products of dx_e = tab[e].x - px ------------------------------------
-    fe acc;
-#pragma unroll 1
-    for (int e = 0; e < KH_TAB_ENTRIES; e++) {
-      fe gx, dx;
-      tab_load_x(gx, tab, e);
-      fe_sub(dx, gx, px);
-      if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
-      if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
-    }
-#ifndef KH_X_NOFWD
-    if (fe_is_zero(acc)) {                           // cold (see the comment above walk_batches)
+    if (fe_is_zero(acc)) {                           // cold, before the batch (see above)
       fe gx0;
       tab_load_x(gx0, tab, 0);
       if (fe_eq(gx0, px)) acc = walk_cold_product(tab, wp.scratch, wp.T, t, px);   // the hop entry alone may be the culprit
       if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
-      // the centre move cannot ride in this batch: done here, parked in the centres array (picked up at e == 0 below)
       if (!walk_cold_move(tab, wp.centers, wp.T, t, px, py)) { walk_flag_or(wp.flags, 1u); break; }
+      walk_flag_or(wp.flags + KH_WALK_FLAG_WORDS + (t >> 5), 1u << (uint32_t)(t & 31));
     }
-#endif
     fe inv;
-    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0
+    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0.  By reference on purpose: inv then
+                        // lives in local memory across the hot loop (one load/store per pair of points) and frees eight
+                        // registers for the hash state; the by-value form measured 5 % slower in the C2 kernel.
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1
@@ -354,7 +243,7 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
         fe_sub(dx, gx, px);
         fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
       } else {
-        dinv = inv;                           // what is left of the batch inverse is 1/dx_0 (cold exceptions: see e == 0 below)
+        dinv = inv;
       }
       if (Emit::PAIRS && e != 0 && e != KH_HALF) {
         // x-only emitters take C+e*S and C-e*S together: two independent multiply chains (ILP) and, in the
@@ -389,19 +278,6 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
             fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
-#ifndef KH_X_NOE0
-            // Cold: what was left of the batch inverse is 0 if the batch had none and exactly 1 if the hop was left out of it
-            // (the product then started from 1).  The centre move was then done before the batch and parked in the centres
-            // array.  No state is carried through the hot loop for this; a genuine 1/dx_0 = 1 fails the second test.
-            if (((dinv.v[0] & ~1u) | dinv.v[1] | dinv.v[2] | dinv.v[3] | dinv.v[4] | dinv.v[5] | dinv.v[6] | dinv.v[7]) == 0) {
-              fe d0;
-              fe_sub(d0, gx, px);
-              if (fe_is_zero(dinv) || fe_is_zero(d0)) {
-#pragma unroll
-                for (int l = 0; l < 8; l++) { x3.v[l] = wp.centers[(uint64_t)l * wp.T + t]; y3.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
-              }
-            }
-#endif
             px = x3; py = y3;
             do_emit = false;
             idx = 0;
@@ -418,22 +294,21 @@ KH_HD void walk_batches_inloop(const WalkParams &wp, const uint32_t *tab, uint64
         if (do_emit) emit.point(x3, y3, batch, idx);
       }
     }
+    // cold, after the batch: what was left of the batch inverse is 1/dx_0 — unless the batch had no inverse (0) or the hop was
+    // left out of it (exactly 1: the product then started from 1).  The loop above has then moved the centre with a useless
+    // slope; the right one was parked before the batch.  (A genuine 1/dx_0 = 1 has no mark and keeps its centre.)
+    if (((inv.v[0] & ~1u) | inv.v[1] | inv.v[2] | inv.v[3] | inv.v[4] | inv.v[5] | inv.v[6] | inv.v[7]) == 0) {
+      uint32_t *mark = wp.flags + KH_WALK_FLAG_WORDS + (t >> 5);
+      if ((*mark >> (uint32_t)(t & 31)) & 1u) {
+        walk_flag_and(mark, ~(1u << (uint32_t)(t & 31)));
+#pragma unroll
+        for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
+      }
+    }
   }
 #pragma unroll
   for (int l = 0; l < 8; l++) { wp.centers[(uint64_t)l * wp.T + t] = px.v[l]; wp.centers[(uint64_t)(8 + l) * wp.T + t] = py.v[l]; }
 }
 
-
-// Which loop shape a kernel uses is a property of its emitter (Emit::WALK_INLOOP): both are the same arithmetic; ptxas
-// allocates registers differently around them and the hash-heavy kernels are sensitive to that (A/B in DESIGN.md §4).
-// -DKH_WALK_SHAPE=0 / 1 forces the peeled / in-loop form everywhere (A/B builds).
-template <class Emit>
-KH_HD void walk_run(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
-#if defined(KH_WALK_SHAPE)
-  if (KH_WALK_SHAPE) walk_batches_inloop(wp, tab, t, emit); else walk_batches(wp, tab, t, emit);
-#else
-  if (Emit::WALK_INLOOP) walk_batches_inloop(wp, tab, t, emit); else walk_batches(wp, tab, t, emit);
-#endif
-}
 
 }  // namespace kh

@@ -17,17 +17,7 @@
 
 using namespace kh;
 
-// loop shape of the walk for the next calls: 0 = peeled (walk_batches), 1 = in-loop (walk_batches_inloop); the kernels pick
-// one per emitter, the tests run both
-static int g_walk_shape = 0;
-template <class Emit>
-static void ds_walk(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &e) {
-  if (g_walk_shape) walk_batches_inloop(wp, tab, t, e); else walk_batches(wp, tab, t, e);
-}
-
 extern "C" {
-
-void ds_set_walk_shape(int s) { g_walk_shape = s; }
 
 void ds_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_mul(r, x, y); fe_to_be(out, r); }
 void ds_fe_sqr(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_sqr(r, x); fe_to_be(out, r); }
@@ -74,7 +64,7 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
 }
 
 // WalkParams::flags of the emulated launches: [0] walker-at-infinity bit, [1] collapsed batches
-static uint32_t g_walk_flags[2] = {0, 0};
+static uint32_t g_walk_flags[KH_WALK_FLAG_WORDS + 64] = {0};   // + the parked-centre marks of up to 2048 walkers
 void ds_walk_flags(uint32_t out[2], int reset) { out[0] = g_walk_flags[0]; out[1] = g_walk_flags[1]; if (reset) g_walk_flags[0] = g_walk_flags[1] = 0; }
 
 // -m vanity for the next ds_scan calls: van = 2048-word prefix bitmap + n x (A[5], B[5]) big-endian words (ScanTargets::van); n = 0 switches it off
@@ -126,22 +116,22 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
     wp.batch_base = base;
     for (uint64_t t = 0; t < T; t++) {
       switch (kind + (endo ? 8 : 0) + (g_van_n ? 16 : 0)) {
-        case 16 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, false, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 16 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, false, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 16 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, false, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 24 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 24 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 24 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 8 + KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 8 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 8 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 8 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
-        case 8 + KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH, true> e(tg); ds_walk(wp, gtab.data(), t, e); break; }
+        case 16 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 16 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 16 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, false, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 24 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_XPOINT: { ScanEmit<KH_SCAN_XPOINT, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_COMP:   { ScanEmit<KH_SCAN_COMP, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_UNCOMP: { ScanEmit<KH_SCAN_UNCOMP, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_BOTH:   { ScanEmit<KH_SCAN_BOTH, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
+        case 8 + KH_SCAN_ETH:    { ScanEmit<KH_SCAN_ETH, true> e(tg); walk_batches(wp, gtab.data(), t, e); break; }
         default: return -1;
       }
     }
@@ -183,7 +173,7 @@ void ds_walk_dump(const uint8_t start[32], const uint8_t stride[32], uint64_t n_
   DumpEmit e; e.out = out;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;
-    for (uint64_t t = 0; t < T; t++) ds_walk(wp, gtab.data(), t, e);
+    for (uint64_t t = 0; t < T; t++) walk_batches(wp, gtab.data(), t, e);
   }
 }
 

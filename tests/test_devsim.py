@@ -18,14 +18,6 @@ class DsHit(C.Structure):
     _fields_ = [("index", C.c_uint64), ("kind", C.c_uint32), ("matched", C.c_uint8 * 20), ("variant", C.c_uint32)]
 
 
-@pytest.fixture(autouse=True, params=[0, 1], ids=["peeled", "inloop"])
-def walk_shape(request, ds):
-    """every test runs with both loop shapes of the walk (walk.cuh: walk_batches / walk_batches_inloop)"""
-    ds.ds_set_walk_shape(request.param)
-    yield request.param
-    ds.ds_set_walk_shape(0)
-
-
 @pytest.fixture(scope="module")
 def ds():
     d = os.path.join(HERE, "devsim")
