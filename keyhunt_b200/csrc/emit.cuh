@@ -216,12 +216,14 @@ struct BsgsTables {
 // One random 4-byte read of the baby-point prefix bitmap (64 GB at -k 512) per giant step.  ncu (profiles/r02_giant_*): L1 asks
 // L2 for ONE 32-byte sector per probe, but L2 looks up and fetches all FOUR sectors of the 128-byte line from DRAM
 // (lts__t_sectors_srcunit_tex_op_read = 4 x lts__t_requests; dram__sectors_read = the same) — the 145 B per giant step are L2
-// sector promotion, not page-table reads.  KH_PRE_LD selects the load flavour (A/B):
+// sector promotion, not page-table reads.  With the .L2::64B qualifier L2 fetches two sectors: 81 B per giant step instead of
+// 145 B (21.9 GB instead of 39.0 GB per 2^28 steps) — and the kernel takes exactly as long (13.74 vs 13.78 ms): it is bound by
+// the EC arithmetic, not by this traffic.  The smaller fetch is kept for the HBM power it saves.  KH_PRE_LD selects the flavour:
 //   0 = ld.global.nc (LDG.CONSTANT)   1 = ld.global.nc.L2::64B   2 = ld.global.L2::64B   3 = ld.global.cv
 //   4 = ld.global.cg                  5 = atom.global.or.b32 with 0 (L2 atomic unit works on 32-byte sectors)
 //   6 = ld.global.nc.L1::no_allocate.L2::64B
 #ifndef KH_PRE_LD
-#define KH_PRE_LD 0
+#define KH_PRE_LD 1
 #endif
 KH_HD uint32_t kh_ld_probe32(const uint32_t *p) {
 #if defined(__CUDA_ARCH__)

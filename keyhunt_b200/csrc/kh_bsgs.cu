@@ -316,7 +316,7 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
   fill_tables(c, bt);
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
-  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0; wp.flags = c->d_flags;
+  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
   kh_time_begin(c);
   uint64_t launches = 0;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
@@ -329,16 +329,6 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
   c->stats.points += d.m;
   c->stats.walker_threads = T;
   KH_CUDA(c, cudaGetLastError());
-  {
-    uint32_t wflags[2] = {0, 0};
-    KH_CUDA(c, cudaMemcpyAsync(wflags, c->d_flags, sizeof(wflags), cudaMemcpyDeviceToHost, c->stream));
-    KH_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (wflags[0] | wflags[1]) {   // cannot happen for baby steps 1..m (m << n); checked so that it would be loud
-      cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(uint32_t), c->stream);
-      free_bsgs(c);
-      return kh_fail(c, KH_EINVAL, "baby-step walk degenerated (flags %u, %u)", wflags[0], wflags[1]);
-    }
-  }
 
   // sort + AMP tables
   kh_time_begin(c);
@@ -487,7 +477,7 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
 
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
-  wp.T = T; wp.n_batches = n_batches; wp.pad = 0; wp.flags = c->d_flags;
+  wp.T = T; wp.n_batches = n_batches; wp.pad = 0;
   // a found key ends the search (keyhunt.cpp:4644 `bsgs_found[k] == 0`): keep one launch to about 2^29 giant steps
   // (~50 ms) so that the check between launches is fine-grained
   {
@@ -504,18 +494,10 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
     wp.batch_base = base;
     kh_time_begin(c);
     kh_giant_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, gp);
-    uint32_t h[2] = {0, 0}, wflags[2] = {0, 0};
+    uint32_t h[2] = {0, 0};
     cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(wflags, c->d_flags, sizeof(wflags), cudaMemcpyDeviceToHost, c->stream);
     c->stats.walk_ms += kh_time_end(c);
     c->stats.walk_launches += 1;
-    if (wflags[0] | wflags[1]) {
-      // a giant step that is the point at infinity (the key sits exactly on the giant-step grid): its batch collapses
-      // like the reference's; a walker whose CENTRE is infinity cannot continue
-      cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(uint32_t), c->stream);
-      c->stats.collapsed_batches += wflags[1];
-      if (wflags[0]) { result = kh_fail(c, KH_EINVAL, "a giant-step walker reached the point at infinity"); break; }
-    }
     const uint64_t covered = std::min<uint64_t>(n_batches - base, (uint64_t)wp.steps * T) * KH_GRP;
     steps_done += covered;
     cudaError_t e = cudaGetLastError();

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <numeric>
 
+#include "plan.hpp"
 #include "scan_kernel.cuh"
 
 using namespace kh;
@@ -28,7 +29,8 @@ __global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *g
   } else if (i < KH_TAB_ENTRIES + ws.T) {
     const uint64_t t = i - KH_TAB_ENTRIES;
     fe cx, cy;
-    if (!setup_center(cx, cy, ws, t)) atomicOr(flags, 1u);
+    // (an idle walker — its first batch lies beyond the segment — may sit anywhere, infinity included)
+    if (!setup_center(cx, cy, ws, t) && (ws.n_batches == 0 || ws.first_batch + t < ws.n_batches)) atomicOr(flags, 1u);
 #pragma unroll
     for (int l = 0; l < 8; l++) { centers[(uint64_t)l * ws.T + t] = cx.v[l]; centers[(uint64_t)(8 + l) * ws.T + t] = cy.v[l]; }
   }
@@ -91,15 +93,14 @@ uint64_t kh_pick_T(kh_ctx *c, uint64_t n_batches) {
 
 int kh_ensure_walk_buffers(kh_ctx *c, uint64_t T) {
   if (!c->d_gtab) KH_CUDA(c, cudaMalloc(&c->d_gtab, KH_TAB_WORDS * sizeof(uint32_t)));
+  if (!c->d_flags) {
+    KH_CUDA(c, cudaMalloc(&c->d_flags, 16 * sizeof(uint32_t)));
+    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(uint32_t), c->stream));
+  }
   if (T > c->T_alloc) {
     if (c->d_centers) cudaFree(c->d_centers);
     if (c->d_scratch) cudaFree(c->d_scratch);
-    if (c->d_flags) cudaFree(c->d_flags);
-    c->d_centers = nullptr; c->d_scratch = nullptr; c->d_flags = nullptr; c->T_alloc = 0;
-    // walk flags: KH_WALK_FLAG_WORDS counters + one "centre parked" mark per walker (walk.cuh)
-    const size_t flag_words = KH_WALK_FLAG_WORDS + (T + 31) / 32;
-    KH_CUDA(c, cudaMalloc(&c->d_flags, flag_words * sizeof(uint32_t)));
-    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, flag_words * sizeof(uint32_t), c->stream));
+    c->d_centers = nullptr; c->d_scratch = nullptr; c->T_alloc = 0;
     KH_CUDA(c, cudaMalloc(&c->d_centers, 16 * T * sizeof(uint32_t)));
     KH_CUDA(c, cudaMalloc(&c->d_scratch, (size_t)1024 * T * sizeof(kh_u4)));
     c->T_alloc = T;
@@ -425,10 +426,7 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   if (n_points == 0 || (n_points % KH_GRP) != 0) return kh_fail(c, KH_EINVAL, "n_points must be a positive multiple of 1024");
   cudaSetDevice(c->device);
   const uint64_t n_batches = n_points / KH_GRP;
-  const uint64_t T = kh_pick_T(c, n_batches);
-  int rc = kh_ensure_walk_buffers(c, T);
-  if (rc) return rc;
-  rc = ensure_hit_buffer(c);
+  int rc = ensure_hit_buffer(c);
   if (rc) return rc;
 
   WalkSetup ws;
@@ -438,22 +436,26 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   bool stride_zero = true;
   for (int i = 0; i < 8; i++) stride_zero &= (ws.s.v[i] == 0);
   if (stride_zero) return kh_fail(c, KH_EINVAL, "stride is zero");
+  const uint64_t T_cap = kh_pick_T(c, n_batches);
   // scalars are plain 256-bit integers on the device (u256_add_mul64 works mod 2^256, k*G needs no reduction mod n):
   // the largest one a scan forms is start + stride*(n_points + T*1024) (the hop W = T*1024*S); refuse ranges where
   // that wraps instead of walking wrong points
   {
     unsigned __int128 carry = 0;
-    const uint64_t reach = n_points + T * (uint64_t)KH_GRP;
-    bool wraps = false;
+    const uint64_t reach = n_points + (T_cap + 4 * KH_T_ALIGN) * (uint64_t)KH_GRP;
     for (int i = 0; i < 8; i++) {
       carry += (unsigned __int128)ws.s.v[i] * reach + ws.k0.v[i];
       carry >>= 32;
     }
-    wraps = carry != 0;
-    if (wraps) return kh_fail(c, KH_EINVAL, "start + stride*n_points reaches 2^256");
+    if (carry != 0) return kh_fail(c, KH_EINVAL, "start + stride*n_points reaches 2^256");
   }
-  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
-  rc = kh_run_setup(c, ws);
+  // the batches of this scan as segments that the kernels can walk without ever meeting a zero difference in the middle of a
+  // walk (plan.hpp): almost always ONE segment with T = T_cap walkers
+  std::vector<ScanSegment> plan;
+  if (!plan_scan(ws.k0, ws.s, n_batches, T_cap, KH_T_ALIGN, plan)) return kh_fail(c, KH_EINVAL, "stride is 0 mod n");
+  uint64_t T_max = 0;
+  for (const ScanSegment &sg : plan) T_max = std::max(T_max, sg.T);
+  rc = kh_ensure_walk_buffers(c, T_max);
   if (rc) return rc;
 
   ScanTargets tg;
@@ -465,46 +467,45 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   tg.table = c->d_table; tg.n = c->n_targets;
   tg.sink.hits = c->d_hits; tg.sink.count = c->d_hit_count; tg.sink.cap = c->hits_alloc; tg.sink.pad = 0;
 
-  WalkParams wp;
-  wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
-  wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0; wp.flags = c->d_flags;
-
-  kh_time_begin(c);
   uint64_t launches = 0;
-  for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
-    wp.batch_base = base;
-    cudaError_t e;
-    if (vanity) e = kh_launch_vanity(c, c->scan_kind, wp, tg);
-    else switch (c->scan_kind) {
-      case KH_SCAN_XPOINT: e = launch_scan<KH_SCAN_XPOINT>(c, wp, tg); break;
-      case KH_SCAN_COMP: e = launch_scan<KH_SCAN_COMP>(c, wp, tg); break;
-      case KH_SCAN_UNCOMP: e = launch_scan<KH_SCAN_UNCOMP>(c, wp, tg); break;
-      case KH_SCAN_BOTH: e = launch_scan<KH_SCAN_BOTH>(c, wp, tg); break;
-      default: e = launch_scan<KH_SCAN_ETH>(c, wp, tg); break;
+  for (const ScanSegment &sg : plan) {
+    const uint64_t T = sg.T;
+    ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = sg.first; ws.n_batches = sg.end;
+    rc = kh_run_setup(c, ws);
+    if (rc) return rc;
+    WalkParams wp;
+    wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
+    wp.T = T; wp.n_batches = sg.end; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+    kh_time_begin(c);
+    for (uint64_t base = sg.first; base < sg.end; base += (uint64_t)wp.steps * T) {
+      wp.batch_base = base;
+      cudaError_t e;
+      if (vanity) e = kh_launch_vanity(c, c->scan_kind, wp, tg);
+      else switch (c->scan_kind) {
+        case KH_SCAN_XPOINT: e = launch_scan<KH_SCAN_XPOINT>(c, wp, tg); break;
+        case KH_SCAN_COMP: e = launch_scan<KH_SCAN_COMP>(c, wp, tg); break;
+        case KH_SCAN_UNCOMP: e = launch_scan<KH_SCAN_UNCOMP>(c, wp, tg); break;
+        case KH_SCAN_BOTH: e = launch_scan<KH_SCAN_BOTH>(c, wp, tg); break;
+        default: e = launch_scan<KH_SCAN_ETH>(c, wp, tg); break;
+      }
+      if (e != cudaSuccess) return kh_fail(c, KH_ENODEV, "scan launch: %s", cudaGetErrorString(e));
+      launches++;
     }
-    if (e != cudaSuccess) return kh_fail(c, KH_ENODEV, "scan launch: %s", cudaGetErrorString(e));
-    launches++;
+    c->stats.walk_ms += kh_time_end(c);
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return kh_fail(c, KH_ENODEV, "scan kernel: %s", cudaGetErrorString(e));
+    }
+    c->stats.collapsed_batches += sg.collapsed;
+    c->stats.walker_threads = std::max<uint64_t>(T, (&sg == &plan[0]) ? 0 : c->stats.walker_threads);
   }
-  const double ms = kh_time_end(c);
-  {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return kh_fail(c, KH_ENODEV, "scan kernel: %s", cudaGetErrorString(e));
-  }
-  c->stats.walk_ms += ms;
   c->stats.walk_launches += launches;
   c->stats.points += n_points;
-  c->stats.walker_threads = T;
 
   // collect raw hits of this scan and convert them while start/stride are at hand
-  uint32_t count = 0, wflags[2] = {0, 0};
+  uint32_t count = 0;
   KH_CUDA(c, cudaMemcpyAsync(&count, c->d_hit_count, sizeof(count), cudaMemcpyDeviceToHost, c->stream));
-  KH_CUDA(c, cudaMemcpyAsync(wflags, c->d_flags, sizeof(wflags), cudaMemcpyDeviceToHost, c->stream));
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (wflags[0] | wflags[1]) {
-    KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(uint32_t), c->stream));
-    c->stats.collapsed_batches += wflags[1];
-    if (wflags[0]) return kh_fail(c, KH_EINVAL, "a walker reached the point at infinity (range touches key 0 mod n)");
-  }
   if (count) {
     if (count > c->hits_alloc) { c->overflowed = true; count = c->hits_alloc; }
     std::vector<RawHit> raw(count);

@@ -25,6 +25,7 @@ struct WalkSetup {
   uint32_t pad;
   uint64_t T;        // walker threads
   uint64_t first_batch;
+  uint64_t n_batches; // walkers whose first batch is >= n_batches are idle (0 = every walker is live)
 };
 
 // table entry e (0 = W = T*1024*S ; e >= 1 : e*S)  ->  16 words (x limbs, y limbs)

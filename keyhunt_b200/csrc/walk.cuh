@@ -42,10 +42,7 @@ struct WalkParams {
   uint64_t n_batches;     // batches in the whole range; batch b is processed iff b < n_batches
   uint32_t steps;         // steps of this launch
   uint32_t pad;
-  uint32_t *flags;        // [0] bit 0: a walker reached the point at infinity; [1]: batches whose shared inverse did not exist;
-                          // [KH_WALK_FLAG_WORDS + t/32] bit t%32: walker t has a centre parked in `centers` (see walk_batches)
 };
-#define KH_WALK_FLAG_WORDS 16
 
 KH_HD void tab_load(fe &gx, fe &gy, const uint32_t *tab, int e) {
   const uint32_t *p = tab + 16 * e;
@@ -78,29 +75,6 @@ KH_HD void scratch_store(kh_u4 *s, uint64_t T, uint64_t t, int e, const fe &a) {
   s[(uint64_t)(2 * e + 1) * T + t] = hi;
 #endif
 }
-// KH_SCRATCH_PREFETCH = D > 0 (A/B knob): at the top of backward iteration e, prefetch the prefix product that iteration
-// e - D will load (a line of the [entry][thread] scratch array), so that its HBM latency is not exposed to the first
-// multiplication of that iteration (ncu: long_scoreboard 1.2 warps per issue cycle in the x-only walk).
-#ifndef KH_SCRATCH_PREFETCH
-#define KH_SCRATCH_PREFETCH 0
-#endif
-KH_HD void scratch_prefetch(const kh_u4 *s, uint64_t T, uint64_t t, int e) {
-#if defined(__CUDA_ARCH__) && KH_SCRATCH_PREFETCH
-  if (e >= 0) {
-    const uint4 *p0 = reinterpret_cast<const uint4 *>(s) + (uint64_t)(2 * e) * T + t;
-    const uint4 *p1 = reinterpret_cast<const uint4 *>(s) + (uint64_t)(2 * e + 1) * T + t;
-#if defined(KH_SCRATCH_PREFETCH_L2)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
-#else
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p0));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1));
-#endif
-  }
-#else
-  (void)s; (void)T; (void)t; (void)e;
-#endif
-}
 KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
 #if defined(__CUDA_ARCH__)
   uint4 lo = reinterpret_cast<const uint4 *>(s)[(uint64_t)(2 * e) * T + t];
@@ -111,90 +85,9 @@ KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
   a.v[0] = lo.x; a.v[1] = lo.y; a.v[2] = lo.z; a.v[3] = lo.w; a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
 }
 
-KH_HD void walk_flag_or(uint32_t *p, uint32_t v) {
-#ifdef __CUDA_ARCH__
-  atomicOr(p, v);
-#else
-  *p |= v;
-#endif
-}
-KH_HD void walk_flag_inc(uint32_t *p) {
-#ifdef __CUDA_ARCH__
-  atomicAdd(p, 1u);
-#else
-  (*p)++;
-#endif
-}
-KH_HD void walk_flag_and(uint32_t *p, uint32_t v) {
-#ifdef __CUDA_ARCH__
-  atomicAnd(p, v);
-#else
-  *p &= v;
-#endif
-}
-
-// Cold helper (by value: its operands must not become address-taken locals of the walk): the batch product WITHOUT the hop
-// entry, prefix products rewritten accordingly.  Only called when the shared product was zero because the centre is +-W.
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__
-#else
-static
-#endif
-fe walk_cold_product(const uint32_t *tab, kh_u4 *scratch, uint64_t T, uint64_t t, fe px) {
-  fe acc;
-  fe_set_u32(acc, 1);
-#pragma unroll 1
-  for (int e = 0; e < KH_TAB_ENTRIES; e++) {
-    if (e > 0) { fe gx, dx; tab_load_x(gx, tab, e); fe_sub(dx, gx, px); fe_mul_cold(acc, acc, dx); }
-    if (e < KH_TAB_ENTRIES - 1) scratch_store(scratch, T, t, e, acc);
-  }
-  return acc;
-}
-
-// Cold helper (by value, see above): the centre move C + W with an inverse of its own — the tangent when C = W.  The new
-// centre is parked in the walker's slot of the centres array in global memory, so that nothing has to stay in registers
-// across the batch.  Returns false when C = -W: the next centre would be the point at infinity.
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__
-#else
-static
-#endif
-bool walk_cold_move(const uint32_t *tab, uint32_t *centers, uint64_t T, uint64_t t, fe px, fe py) {
-  fe gx, gy, dx, dy, inv, s, s2, x3, y3;
-  tab_load(gx, gy, tab, 0);
-  fe_sub(dx, gx, px);
-  fe_sub(dy, gy, py);
-  if (fe_is_zero(dx)) {
-    if (!fe_is_zero(dy)) return false;
-    fe_mul_cold(s2, px, px); fe_add(dy, s2, s2); fe_add(dy, dy, s2);     // slope 3x^2 / 2y
-    fe_add(dx, py, py);
-  }
-  fe_inv(inv, dx);
-  fe_mul_cold(s, dy, inv);
-  fe_mul_cold(s2, s, s);
-  fe_sub(x3, s2, px);
-  fe_sub(x3, x3, gx);
-  fe_sub(y3, gx, x3); fe_mul_cold(y3, y3, s); fe_sub(y3, y3, gy);
-#pragma unroll
-  for (int l = 0; l < 8; l++) { centers[(uint64_t)l * T + t] = x3.v[l]; centers[(uint64_t)(8 + l) * T + t] = y3.v[l]; }
-  return true;
-}
-
 // Walks `steps` batches for walker thread t.  `tab` is the table in shared memory (device) or plain
 // memory (host test build).  For each point calls emit.point(x, y, batch, idx) where key index in the
 // range is batch*1024 + idx; y is valid only if Emit::NEED_Y.
-//
-// Zero differences.  A dx_e = 0 makes the shared product zero, and fe_inv(0) = 0 (like Int::ModInv): every slope of the
-// batch is then 0 and its points are garbage — exactly what IntGroup::ModInv does to the reference's batch when its centre
-// is +-e*S (a range touching key 0 mod n); the centre itself (pts[512]) is still right in both.  Two
-// things the reference does not have and that therefore must not go wrong here:
-//   * the hop entry: a centre equal to W (`-r 200:...` puts walker T-1 there) would zero the product although the
-//     reference's batch is fine -> the batch product is redone without entry 0;
-//   * the centre move: it must never come out of a zero or missing inverse -> it is done with an inverse of its own (the
-//     tangent when C = W) and parked in the centres array; C = -W (the next centre is the point at infinity) raises flags[0].
-// All of that happens BEFORE the batch, in out-of-line helpers, when the batch product turns out to be zero, plus one
-// state-free test AFTER the batch; the hot loop itself is untouched (an in-loop test cost the C2 kernel 3 %, moving the centre
-// out of the loop 4.6 %: the hash kernels sit at the 128-register cap and ptxas allocates differently around any change).
 template <class Emit>
 KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
   constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
@@ -217,18 +110,8 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
-    if (fe_is_zero(acc)) {                           // cold, before the batch (see above)
-      fe gx0;
-      tab_load_x(gx0, tab, 0);
-      if (fe_eq(gx0, px)) acc = walk_cold_product(tab, wp.scratch, wp.T, t, px);   // the hop entry alone may be the culprit
-      if (fe_is_zero(acc)) walk_flag_inc(wp.flags + 1);
-      if (!walk_cold_move(tab, wp.centers, wp.T, t, px, py)) { walk_flag_or(wp.flags, 1u); break; }
-      walk_flag_or(wp.flags + KH_WALK_FLAG_WORDS + (t >> 5), 1u << (uint32_t)(t & 31));
-    }
     fe inv;
-    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move); inv(0) = 0.  By reference on purpose: inv then
-                        // lives in local memory across the hot loop (one load/store per pair of points) and frees eight
-                        // registers for the hash state; the by-value form measured 5 % slower in the C2 kernel.
+    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move)
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1
@@ -238,7 +121,6 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e > 0) {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
-        scratch_prefetch(wp.scratch, wp.T, t, e - 1 - KH_SCRATCH_PREFETCH);
         fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
         fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
@@ -294,21 +176,9 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
         if (do_emit) emit.point(x3, y3, batch, idx);
       }
     }
-    // cold, after the batch: what was left of the batch inverse is 1/dx_0 — unless the batch had no inverse (0) or the hop was
-    // left out of it (exactly 1: the product then started from 1).  The loop above has then moved the centre with a useless
-    // slope; the right one was parked before the batch.  (A genuine 1/dx_0 = 1 has no mark and keeps its centre.)
-    if (((inv.v[0] & ~1u) | inv.v[1] | inv.v[2] | inv.v[3] | inv.v[4] | inv.v[5] | inv.v[6] | inv.v[7]) == 0) {
-      uint32_t *mark = wp.flags + KH_WALK_FLAG_WORDS + (t >> 5);
-      if ((*mark >> (uint32_t)(t & 31)) & 1u) {
-        walk_flag_and(mark, ~(1u << (uint32_t)(t & 31)));
-#pragma unroll
-        for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
-      }
-    }
   }
 #pragma unroll
   for (int l = 0; l < 8; l++) { wp.centers[(uint64_t)l * wp.T + t] = px.v[l]; wp.centers[(uint64_t)(8 + l) * wp.T + t] = py.v[l]; }
 }
-
 
 }  // namespace kh

@@ -14,6 +14,7 @@
 
 #include "../../keyhunt_b200/csrc/emit.cuh"
 #include "../../keyhunt_b200/csrc/setup.cuh"
+#include "../../keyhunt_b200/csrc/plan.hpp"
 
 using namespace kh;
 
@@ -63,9 +64,27 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
   scratch.resize((size_t)1024 * ws.T);
 }
 
-// WalkParams::flags of the emulated launches: [0] walker-at-infinity bit, [1] collapsed batches
-static uint32_t g_walk_flags[KH_WALK_FLAG_WORDS + 64] = {0};   // + the parked-centre marks of up to 2048 walkers
-void ds_walk_flags(uint32_t out[2], int reset) { out[0] = g_walk_flags[0]; out[1] = g_walk_flags[1]; if (reset) g_walk_flags[0] = g_walk_flags[1] = 0; }
+// the plan of the last emulated scan (plan.hpp): out[0] = segments, out[1] = collapsed batches, out[2] = distinct T values
+static std::vector<ScanSegment> g_last_plan;
+void ds_last_plan(uint64_t out[3]) {
+  out[0] = g_last_plan.size(); out[1] = 0;
+  std::vector<uint64_t> ts;
+  for (const ScanSegment &sg : g_last_plan) { out[1] += sg.collapsed; ts.push_back(sg.T); }
+  std::sort(ts.begin(), ts.end());
+  out[2] = (uint64_t)(std::unique(ts.begin(), ts.end()) - ts.begin());
+}
+// 1 if plan.hpp's constant really is 1024^-1 mod n
+int ds_plan_selfcheck(void) {
+  u256 one, z;
+  u256_set_u64(one, 1); u256_set_u64(z, 0);
+  const ScanGeometry g = plan_geometry(z, one);
+  u256 k;
+  u256_set_u64(k, 1024);
+  u256 r;
+  u256_mulmod_n(r, g.inv1024, k);
+  for (int i = 1; i < 8; i++) if (r.v[i]) return 0;
+  return r.v[0] == 1;
+}
 
 // -m vanity for the next ds_scan calls: van = 2048-word prefix bitmap + n x (A[5], B[5]) big-endian words (ScanTargets::van); n = 0 switches it off
 static const uint32_t *g_van = nullptr;
@@ -74,16 +93,17 @@ void ds_set_vanity(const uint32_t *van, uint32_t n) { g_van = van; g_van_n = n; 
 
 // kind: KH_SCAN_*; table20: N sorted 20-byte records; bloom image as bytes
 int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint8_t *bloom_bytes, uint64_t bloom_bits,
-                uint32_t bloom_hashes, const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T,
+                uint32_t bloom_hashes, const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T_cap,
                 uint32_t steps_per_launch, DsHit *out, uint32_t max_hits, int endo) {
   WalkSetup ws;
   memset(&ws, 0, sizeof(ws));
   u256_from_be(ws.s, stride);
   u256_from_be(ws.k0, start);
-  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
+  ws.q.inf = 1; ws.neg = 0;
+  // what kh_scan does: the batches as segments (almost always one), T walkers at most
+  if (!plan_scan(ws.k0, ws.s, n_batches, T_cap, 1, g_last_plan)) return -2;
   std::vector<uint32_t> gtab, centers;
   std::vector<kh_u4> scratch;
-  make_walk(ws, gtab, centers, scratch);
 
   std::vector<uint32_t> table(5 * n_targets);
   for (uint64_t i = 0; i < n_targets; i++)
@@ -109,10 +129,14 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
     tg.pre = bm.data(); tg.pre_k = k;
   }
 
+  for (const ScanSegment &sg : g_last_plan) {
+  const uint64_t T = sg.T;
+  ws.T = T; ws.first_batch = sg.first; ws.n_batches = sg.end;
+  make_walk(ws, gtab, centers, scratch);
   WalkParams wp;
   wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
-  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch; wp.pad = 0; wp.flags = g_walk_flags;
-  for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
+  wp.T = T; wp.n_batches = sg.end; wp.steps = steps_per_launch; wp.pad = 0;
+  for (uint64_t base = sg.first; base < sg.end; base += (uint64_t)steps_per_launch * T) {
     wp.batch_base = base;
     for (uint64_t t = 0; t < T; t++) {
       switch (kind + (endo ? 8 : 0) + (g_van_n ? 16 : 0)) {
@@ -136,6 +160,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
       }
     }
   }
+  }
   uint32_t n = count < max_hits ? count : max_hits;
   for (uint32_t i = 0; i < n; i++) {
     out[i].index = raw[i].batch * KH_GRP + raw[i].idx;
@@ -158,22 +183,26 @@ struct DumpEmit {
     fe_to_be(p, x); fe_to_be(p + 32, y);
   }
 };
-void ds_walk_dump(const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T, uint32_t steps_per_launch, uint8_t *out) {
+void ds_walk_dump(const uint8_t start[32], const uint8_t stride[32], uint64_t n_batches, uint64_t T_cap, uint32_t steps_per_launch, uint8_t *out) {
   WalkSetup ws;
   memset(&ws, 0, sizeof(ws));
   u256_from_be(ws.s, stride);
   u256_from_be(ws.k0, start);
-  ws.q.inf = 1; ws.neg = 0; ws.T = T; ws.first_batch = 0;
+  ws.q.inf = 1; ws.neg = 0;
+  if (!plan_scan(ws.k0, ws.s, n_batches, T_cap, 1, g_last_plan)) return;
   std::vector<uint32_t> gtab, centers;
   std::vector<kh_u4> scratch;
-  make_walk(ws, gtab, centers, scratch);
-  WalkParams wp;
-  wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
-  wp.T = T; wp.n_batches = n_batches; wp.steps = steps_per_launch; wp.pad = 0; wp.flags = g_walk_flags;
   DumpEmit e; e.out = out;
-  for (uint64_t base = 0; base < n_batches; base += (uint64_t)steps_per_launch * T) {
-    wp.batch_base = base;
-    for (uint64_t t = 0; t < T; t++) walk_batches(wp, gtab.data(), t, e);
+  for (const ScanSegment &sg : g_last_plan) {
+    ws.T = sg.T; ws.first_batch = sg.first; ws.n_batches = sg.end;
+    make_walk(ws, gtab, centers, scratch);
+    WalkParams wp;
+    wp.gtab = gtab.data(); wp.centers = centers.data(); wp.scratch = scratch.data();
+    wp.T = sg.T; wp.n_batches = sg.end; wp.steps = steps_per_launch; wp.pad = 0;
+    for (uint64_t base = sg.first; base < sg.end; base += (uint64_t)steps_per_launch * sg.T) {
+      wp.batch_base = base;
+      for (uint64_t t = 0; t < sg.T; t++) walk_batches(wp, gtab.data(), t, e);
+    }
   }
 }
 

@@ -91,21 +91,25 @@ def test_walk_geometry(ds, oracle, start, stride, nb, T, spl):
         assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(start + b * 1024 * stride, stride, True)
 
 
-def _walk_flags(ds):
-    fl = (C.c_uint32 * 2)()
-    ds.ds_walk_flags(fl, 1)
-    return list(fl)
+def _last_plan(ds):
+    out = (C.c_uint64 * 3)()
+    ds.ds_last_plan(out)
+    return dict(segments=out[0], collapsed=out[1], distinct_T=out[2])
+
+
+def test_plan_constant(ds):
+    assert ds.ds_plan_selfcheck() == 1
 
 
 def test_walk_centre_on_the_hop_point(ds, oracle):
-    """start = 512, stride 1, T walkers: walker T-1 starts with its centre ON W = T*1024*G, so the hop's difference is zero
-    (ADVICE r1).  The reference has no such hop: its batch is fine, and so must ours be; the centre then moves by the
-    tangent and the walker's later batches are right as well."""
+    """start = 512, stride 1, T walkers: batch T-1 has its centre ON W = T*1024*G, so the hop's difference would be zero
+    (ADVICE r1).  The reference has no such hop: its batch is fine, and so must ours be: the host plan (plan.hpp) cuts the scan
+    there and walks the rest with another T, the kernels never see the coincidence."""
     T, nb = 4, 12
     out = C.create_string_buffer(nb * 65536)
-    _walk_flags(ds)
     ds.ds_walk_dump(be32(512), be32(1), nb, T, 2, out)
-    assert _walk_flags(ds) == [0, 0]
+    plan = _last_plan(ds)
+    assert plan["collapsed"] == 0 and plan["segments"] == 2 and plan["distinct_T"] == 2
     for b in range(1, nb):
         assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(512 + b * 1024, 1, True), b
     # batch 0 has its centre on 1024*G = the reference's own next-start delta (_2Gn, keyhunt.cpp:3448): the REFERENCE's batch
@@ -114,20 +118,34 @@ def test_walk_centre_on_the_hop_point(ds, oracle):
         x, y = oracle.pubkey(512 + i)
         assert out.raw[64 * i:64 * i + 64] == be32(x) + be32(y)
     assert out.raw[:65536] != oracle.batch_points(512, 1, True)
+    # the same with a stride: start + 512*stride = T*1024*stride  <=>  start = (T*1024 - 512) * stride - 1024*b*stride
+    stride = 977
+    ds.ds_walk_dump(be32(512 * stride), be32(stride), nb, T, 3, out)
+    assert _last_plan(ds)["segments"] == 2
+    for b in range(1, nb):
+        assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(512 * stride + b * 1024 * stride, stride, True), b
 
 
 def test_walk_batch_without_inverse_matches_the_reference(ds, oracle):
     """a range that runs over key 0 (mod n): the centre of a batch is +-512*G, one difference is zero, no shared inverse
     exists.  IntGroup::ModInv then yields zeros and the reference's 1023 non-centre points are deterministic garbage
-    (SURVEY App. B.11); the same garbage comes out here, the batch is counted, and the walker's next batches are right."""
+    (SURVEY App. B.11); the same garbage comes out here (the batch is planned as a segment of its own so that its walker's
+    useless next centre is never used), it is counted, and every other batch is right."""
     start, T, nb = N_ORDER - 1024, 2, 6
     out = C.create_string_buffer(nb * 65536)
-    _walk_flags(ds)
     ds.ds_walk_dump(be32(start), be32(1), nb, T, 3, out)
-    assert _walk_flags(ds) == [0, 2]
+    plan = _last_plan(ds)
+    assert plan["collapsed"] == 2 and plan["segments"] == 3
     for b in range(nb):
         base = start + b * 1024
         assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(base % N_ORDER if b else base, 1, True), b
+
+
+def test_plan_is_a_single_segment_for_ordinary_ranges(ds):
+    out = C.create_string_buffer(3 * 65536)
+    for start, stride in ((1, 1), (0x2000000000000000, 1), (0xDEADBEEF12345, 977), (2**255 + 12345, 2**64 + 1)):
+        ds.ds_walk_dump(be32(start), be32(stride), 3, 2, 2, out)
+        assert _last_plan(ds) == dict(segments=1, collapsed=0, distinct_T=1), (start, stride)
 
 
 KINDS = {"xpoint": (0, MODE_XPOINT, CRYPTO_BTC, SEARCH_COMPRESS), "comp": (1, MODE_RMD160, CRYPTO_BTC, SEARCH_COMPRESS),
