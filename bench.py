@@ -61,20 +61,20 @@ STEP_POINTS = 1 << 32
 # cpu_rate = expected Mkeys/s per host thread of the reference (only used to size its bounded sample).
 WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
-               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu"),
+               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3971),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
                mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162, disp=1,
                cpu_rate=1.4, binding="alu",
-               alu_ops=6830),   # ncu (profiles/r01_prefilter_both_ncu_sections.txt): 42.46 G warp instructions per 2^27 points, ALU share = (86.5 % x 0.5/clk) / 64.1 % issue = 67.5 % -> 6,830 ALU thread-ops per point
+               alu_ops=6993),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 41.90 G warp instructions per 2^27 points, 70.0 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
                mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, disp=1,
-               cpu_rate=4.8, binding="fma_heavy", wide_mults=224),   # 2.5 M + 1 S per point = 2.5 x 72 + 44 IMAD.WIDE
+               cpu_rate=4.8, binding="fma_heavy", wide_mults=246),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
                   mode="address", crypto="btc", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5800 - 2 * 162, disp=2,
-                  cpu_rate=2.4, binding="alu"),
+                  cpu_rate=2.4, binding="alu", alu_ops=3971),
     "c5eth": dict(desc="C5 address ETH, 1024 targets (16 planted), from 0x10000000000",
                   mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162, disp=1,
-                  cpu_rate=2.1, binding="alu"),
+                  cpu_rate=2.1, binding="alu", alu_ops=5546),
 }
 N44 = 1 << 44          # C4: -n 2^44 -k 512 -> m = 2^31 baby steps
 
@@ -435,12 +435,10 @@ def roofline(env, wl, value_pts_s, pts_per_launch, launch_ms, clk):
                              "frac": a / peaks["lop3"], "unit": "Tiop/s"}
     elif "wide_mults" in w:
         a = pts_per_launch * w["wide_mults"] / (launch_ms * 1e-3)
-        mix = (env.pipe or {}).get("imad_wide_in_walk_mix")
         r["binding_pipe"] = {"pipe": "fma_heavy (IMAD.WIDE.U32.X)", "ops_per_point": w["wide_mults"], "achieved": a / 1e12,
                              "peak": peaks["imad_wide"] / 1e12, "frac": a / peaks["imad_wide"], "unit": "Tiop/s",
-                             # carry-chained wide multiply-adds and ALU-pipe ops do not overlap freely (kh_pipe_peak [5], [7]): the
-                             # rate of the same instruction inside the walk's own 1 : 2.2 mix with ALU ops is the practical ceiling
-                             "peak_in_walk_mix": (mix / 1e12) if mix else None, "frac_of_walk_mix": (a / mix) if mix else None}
+                             "note": "wide multiply-adds in carry chains; they do not overlap with ALU-pipe work (kh_pipe_peak: IMAD.WIDE + LOP3 "
+                                     "issued together run at the SUM of their times), so the ~400 ALU ops per point of the walk are not free"}
     return r
 
 
@@ -622,15 +620,15 @@ def run_c4(env, k, steps, W, cpu_k, cpu_seconds):
         "e2e": {"value": st["points"] / wall / 1e6, "unit": "M giant steps/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 48, "steps": steps},
         "gpu_launches": st["walk_launches"] + st["other_launches"], "tier1_positives": st["tier1_positives"],
         "roofline": {"bound": "hbm", "achieved": gs_kernel * 64 / 1e9, "peak": hbm, "unit": "GB/s", "frac": gs_kernel * 64 / 1e9 / hbm,
-                     "traffic": 161.0 * (st["points"] / max(1, st["walk_launches"])),
+                     "traffic": 97.5 * (st["points"] / max(1, st["walk_launches"])),
                      "kernel": "kh_giant_kernel", "bytes_per_giant_step": 64,
                      "note": "algorithmic 64 B/step (SURVEY §8d: 2 random 32-B sectors; here 16 B + 16 B of prefix-product scratch and one 32-B sector of "
-                             "the baby-point prefix bitmap that answers for the tier-1 bloom); ncu measures 145 B read + 16 B written per step "
-                             "(profiles/r01_giant_prefilter_ncu_metrics.csv); co-limited by the FMA-heavy pipe like the xpoint walk",
+                             "the baby-point prefix bitmap that answers for the tier-1 bloom); ncu: 81 B read + 16 B written per step with the 64-byte L2 "
+                             "fetch (145 B with the default 128-byte sector promotion, the SAME kernel time: profiles/r02_giant_probe_flavours.txt) — the "
+                             "kernel is bound by the EC arithmetic like the xpoint walk, not by this traffic",
                      "binding_pipe": ({"pipe": "fma_heavy (IMAD.WIDE.U32.X)", "ops_per_point": 224, "achieved": gs_kernel * 224 / 1e12,
                                        "peak": env.peaks["imad_wide"] / 1e12, "frac": gs_kernel * 224 / env.peaks["imad_wide"], "unit": "Tiop/s",
-                                       "peak_in_walk_mix": ((env.pipe or {}).get("imad_wide_in_walk_mix") or 0) / 1e12 or None,
-                                       "frac_of_walk_mix": (gs_kernel * 224 / env.pipe["imad_wide_in_walk_mix"]) if (env.pipe or {}).get("imad_wide_in_walk_mix") else None}
+                                       "ops_note": "224 wide multiply-adds of the walk per giant step (ncu executes 255 incl. index arithmetic)"}
                                       if env.peaks else None)},
         "cpu_baseline": cpu,
     }
