@@ -153,6 +153,28 @@ KH_HD void ge_mul_g(ge &r, const u256 &k) {
   ge_set_g(g);
   ge_scalar_mul(r, g, k);
 }
+// k*G by a fixed-base comb: comb[(w*256 + d)*16 ..] = d * 2^(8w) * G as 8 x-limbs + 8 y-limbs (d = 1..255, w = 0..31; built
+// once per context by kh_comb_kernel, 512 KB, L2-resident).  At most 32 mixed additions + one inversion instead of 256
+// doublings + ~128 additions: the set-up of a walk (one k*G per walker thread) is 5x shorter, which is what a short
+// kh_bsgs_search call or a server request consists of.  comb == nullptr: the plain double-and-add (host test build).
+#define KH_COMB_WORDS (32 * 256 * 16)
+KH_HD void ge_mul_g_comb(ge &r, const u256 &k, const uint32_t *comb) {
+  if (!comb) { ge_mul_g(r, k); return; }
+  gej acc;
+  gej_set_inf(acc);
+#pragma unroll 1
+  for (int w = 0; w < 32; w++) {
+    const uint32_t d = (k.v[w >> 2] >> (8 * (w & 3))) & 0xFFu;
+    if (!d) continue;
+    const uint32_t *e = comb + (size_t)(w * 256 + d) * 16;
+    ge q;
+#pragma unroll
+    for (int l = 0; l < 8; l++) { q.x.v[l] = e[l]; q.y.v[l] = e[8 + l]; }
+    q.inf = 0;
+    gej_add_ge(acc, acc, q);
+  }
+  gej_to_ge(r, acc);
+}
 KH_HD void ge_neg(ge &r, const ge &p) { r.x = p.x; fe_neg(r.y, p.y); r.inf = p.inf; }
 // full affine addition with every special case (used for start points: Q + k*G)
 KH_HD void ge_add(ge &r, const ge &p, const ge &q) {

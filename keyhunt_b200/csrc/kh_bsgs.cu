@@ -115,6 +115,7 @@ struct RefineParams {
   u256 start;               // range start (base key of window 0)
   uint32_t *found;          // [0] flag
   u256 *found_key;
+  const uint32_t *comb;     // fixed-base comb of G (ec.cuh ge_mul_g_comb)
 };
 
 __device__ __forceinline__ void load_aux_point(ge &p, const uint32_t *aux, int i) {
@@ -130,15 +131,15 @@ __device__ __forceinline__ bool tier_check(const BloomDev &bl, const fe &x) {
   return bloom_test(bl, x.v[7] >> 24, a, b);
 }
 // S = Q - key*G  (AddDirect(Q, Negation(ComputePublicKey(key))), keyhunt.cpp:5163-5171)
-__device__ __noinline__ void q_minus_key(ge &s, const ge &q, const u256 &key) {
+__device__ __noinline__ void q_minus_key(ge &s, const ge &q, const u256 &key, const uint32_t *comb) {
   ge bp;
-  ge_mul_g(bp, key);
+  ge_mul_g_comb(bp, key, comb);
   ge_neg(bp, bp);
   ge_add_direct(s, q, bp);
 }
-__device__ __noinline__ bool key_matches(const ge &q, const u256 &key) {
+__device__ __noinline__ bool key_matches(const ge &q, const u256 &key, const uint32_t *comb) {
   ge p;
-  ge_mul_g(p, key);
+  ge_mul_g_comb(p, key, comb);
   return !p.inf && fe_eq(p.x, q.x);
 }
 
@@ -158,14 +159,14 @@ __global__ void __launch_bounds__(32) kh_refine_kernel(RefineParams rp) {
   // tier-1 positive; the checks below cannot confirm it (they do not see offsets 0..2m of a window), this one does.
   if (rp.base_check && (g % rp.steps_per_window) == 0) {
     ge bp;
-    ge_mul_g(bp, base2);
+    ge_mul_g_comb(bp, base2, rp.comb);
     if (!bp.inf && fe_eq(bp.x, rp.q.x) && fe_eq(bp.y, rp.q.y)) {
       if (lane == 0 && atomicCAS(rp.found, 0u, 1u) == 0u) *rp.found_key = base2;
       return;
     }
   }
   ge S;
-  q_minus_key(S, rp.q, base2);
+  q_minus_key(S, rp.q, base2, rp.comb);
   // tier 2: lane i2 tests S + AMP2[i2]
   ge amp, P2;
   load_aux_point(amp, rp.aux, (int)lane);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(32) kh_refine_kernel(RefineParams rp) {
     { u256 z; u256_set_u64(z, 0); u256_add_mul64(two_m2, z, two_m2, 2); }
     u256_add_mul64(base3, base2, two_m2, (uint64_t)i2);
     ge S3, P3;
-    q_minus_key(S3, rp.q, base3);
+    q_minus_key(S3, rp.q, base3, rp.comb);
     load_aux_point(amp, rp.aux, 32 + (int)lane);
     ge_add_direct(P3, S3, amp);
     // calcualteindex(i3) = (2*i3+1)*m3   (keyhunt.cpp:7859)
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(32) kh_refine_kernel(RefineParams rp) {
         u256 t;
         u256_add_mul64(t, base3, calc, 1);
         u256_add_u64(key, t, j1);                                   // keyhunt.cpp:5212-5219
-        if (key_matches(rp.q, key)) ok = true;
-        else { u256_sub_u64(key, t, j1); if (key_matches(rp.q, key)) ok = true; }   // :5221-5228
+        if (key_matches(rp.q, key, rp.comb)) ok = true;
+        else { u256_sub_u64(key, t, j1); if (key_matches(rp.q, key, rp.comb)) ok = true; }   // :5221-5228
         lo++;
       }
     } else if (fe_eq(S3.x, amp.x)) {                                // keyhunt.cpp:5238-5243
@@ -473,7 +474,7 @@ int kh_bsgs_search(kh_ctx *c, const uint8_t pub_xy_be[64], const uint8_t start_b
   gp.pre = c->d_bsgs_pre; gp.pre_k = c->bsgs_pre_k;
   RefineParams rp;
   rp.bt = bt; rp.aux = c->d_aux_tab; rp.cands = d_cands; rp.n_cands = 0; rp.base_check = (uint32_t)c->bsgs_base_check; rp.steps_per_window = d.aux;
-  rp.q = ws.q; rp.start = start; rp.found = d_cnt + 1; rp.found_key = d_key;
+  rp.q = ws.q; rp.start = start; rp.found = d_cnt + 1; rp.found_key = d_key; rp.comb = c->d_comb;
 
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;

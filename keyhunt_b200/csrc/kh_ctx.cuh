@@ -39,6 +39,7 @@ struct kh_ctx {
   uint32_t *d_centers = nullptr;   // 16*T
   kh::kh_u4 *d_scratch = nullptr;  // 1024*T
   uint32_t *d_flags = nullptr;     // [0] = set-up error flag (centre at infinity)
+  uint32_t *d_comb = nullptr;      // fixed-base comb of G: 32 x 256 points (ec.cuh ge_mul_g_comb), built on first use
 
   // scan targets
   bool have_targets = false;
@@ -99,6 +100,7 @@ static inline int kh_fail(kh_ctx *c, int code, const char *fmt, ...) {
 // implemented in kh_scan.cu, used by kh_bsgs.cu
 int kh_ensure_walk_buffers(kh_ctx *c, uint64_t T);
 uint64_t kh_pick_T(kh_ctx *c, uint64_t n_batches);
-int kh_run_setup(kh_ctx *c, const kh::WalkSetup &ws);
+int kh_run_setup(kh_ctx *c, const kh::WalkSetup &ws);   // (fills in ws.comb itself)
+int kh_ensure_comb(kh_ctx *c);
 void kh_time_begin(kh_ctx *c);
 double kh_time_end(kh_ctx *c);  // ms since kh_time_begin on the context stream (synchronises)

@@ -36,6 +36,21 @@ __global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *g
   }
 }
 
+// fixed-base comb of G (ec.cuh): entry (w, d) = d * 2^(8w) * G, one plain scalar multiplication each, once per context
+__global__ void __launch_bounds__(128) kh_comb_kernel(uint32_t *comb) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 256) return;
+  const uint32_t w = i >> 8, d = i & 255;
+  u256 k;
+#pragma unroll
+  for (int l = 0; l < 8; l++) k.v[l] = 0;
+  k.v[w >> 2] = d << (8 * (w & 3));
+  ge p;
+  ge_mul_g(p, k);
+#pragma unroll
+  for (int l = 0; l < 8; l++) { comb[(size_t)i * 16 + l] = p.x.v[l]; comb[(size_t)i * 16 + 8 + l] = p.y.v[l]; }
+}
+
 // exact prefix bitmap over the first k bits of every target record (ScanTargets::pre)
 __global__ void kh_pre_build(uint32_t *pre, uint32_t k, const uint32_t *table_be, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,11 +71,11 @@ __global__ void kh_bloom_build(BloomDev bl, const uint32_t *table_be, uint64_t n
 struct DevKeyInfo {
   uint32_t x[8], y[8], hc[5], hu[5], eth[5], inf;
 };
-__global__ void __launch_bounds__(64) kh_derive_kernel(const u256 *keys, uint64_t n, DevKeyInfo *out) {
+__global__ void __launch_bounds__(64) kh_derive_kernel(const u256 *keys, uint64_t n, DevKeyInfo *out, const uint32_t *comb) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   ge p;
-  ge_mul_g(p, keys[i]);
+  ge_mul_g_comb(p, keys[i], comb);
   DevKeyInfo r;
 #pragma unroll
   for (int k = 0; k < 8; k++) { r.x[k] = p.x.v[k]; r.y[k] = p.y.v[k]; }
@@ -108,7 +123,22 @@ int kh_ensure_walk_buffers(kh_ctx *c, uint64_t T) {
   return KH_OK;
 }
 
-int kh_run_setup(kh_ctx *c, const WalkSetup &ws) {
+int kh_ensure_comb(kh_ctx *c) {
+  if (c->d_comb) return KH_OK;
+  KH_CUDA(c, cudaMalloc(&c->d_comb, (size_t)KH_COMB_WORDS * sizeof(uint32_t)));
+  kh_time_begin(c);
+  kh_comb_kernel<<<(32 * 256 + 127) / 128, 128, 0, c->stream>>>(c->d_comb);
+  c->stats.setup_ms += kh_time_end(c);
+  c->stats.other_launches += 1;
+  KH_CUDA(c, cudaGetLastError());
+  return KH_OK;
+}
+
+int kh_run_setup(kh_ctx *c, const WalkSetup &ws_in) {
+  int rcc = kh_ensure_comb(c);
+  if (rcc) return rcc;
+  WalkSetup ws = ws_in;
+  ws.comb = c->d_comb;
   const uint64_t n = KH_TAB_ENTRIES + ws.T;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   kh_time_begin(c);
@@ -148,13 +178,17 @@ static int derive_dev(kh_ctx *c, const std::vector<u256> &keys, std::vector<DevK
   const uint64_t n = keys.size();
   out.resize(n);
   if (!n) return KH_OK;
+  {
+    int rcc = kh_ensure_comb(c);
+    if (rcc) return rcc;
+  }
   u256 *d_keys = nullptr;
   DevKeyInfo *d_out = nullptr;
   KH_CUDA(c, cudaMalloc(&d_keys, n * sizeof(u256)));
   if (cudaMalloc(&d_out, n * sizeof(DevKeyInfo)) != cudaSuccess) { cudaFree(d_keys); return kh_fail(c, KH_ENOMEM, "cudaMalloc derive"); }
   cudaMemcpyAsync(d_keys, keys.data(), n * sizeof(u256), cudaMemcpyHostToDevice, c->stream);
   kh_time_begin(c);
-  kh_derive_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_keys, n, d_out);
+  kh_derive_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(d_keys, n, d_out, c->d_comb);
   cudaMemcpyAsync(out.data(), d_out, n * sizeof(DevKeyInfo), cudaMemcpyDeviceToHost, c->stream);
   c->stats.aux_ms += kh_time_end(c);
   c->stats.other_launches += 1;
@@ -197,7 +231,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre, c->d_comb};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);

@@ -26,6 +26,7 @@ struct WalkSetup {
   uint64_t T;        // walker threads
   uint64_t first_batch;
   uint64_t n_batches; // walkers whose first batch is >= n_batches are idle (0 = every walker is live)
+  const uint32_t *comb; // fixed-base comb of G (ec.cuh ge_mul_g_comb), nullptr = plain double-and-add
 };
 
 // table entry e (0 = W = T*1024*S ; e >= 1 : e*S)  ->  16 words (x limbs, y limbs)
@@ -36,7 +37,7 @@ KH_HD void setup_table_entry(uint32_t out[16], const WalkSetup &ws, uint32_t e) 
   const uint64_t mult = (e == 0) ? ws.T * (uint64_t)KH_GRP : (uint64_t)e;
   u256_add_mul64(k, zero, ws.s, mult);
   ge p;
-  ge_mul_g(p, k);
+  ge_mul_g_comb(p, k, ws.comb);
   if (ws.neg) ge_neg(p, p);
 #pragma unroll
   for (int i = 0; i < 8; i++) { out[i] = p.x.v[i]; out[8 + i] = p.y.v[i]; }
@@ -48,7 +49,7 @@ KH_HD bool setup_center(fe &cx, fe &cy, const WalkSetup &ws, uint64_t t) {
   u256 k;
   u256_add_mul64(k, ws.k0, ws.s, (ws.first_batch + t) * (uint64_t)KH_GRP + (uint64_t)KH_HALF);
   ge p;
-  ge_mul_g(p, k);
+  ge_mul_g_comb(p, k, ws.comb);
   if (ws.neg) ge_neg(p, p);
   if (!ws.q.inf) { ge r; ge_add(r, ws.q, p); p = r; }
   cx = p.x; cy = p.y;

@@ -40,3 +40,56 @@ def test_line_follows_the_contract(path):
     if "keys_per_step_per_gpu" in d["config"]:
         per_step = d["config"]["keys_per_step_per_gpu"] * d["n_gpus"]
         assert abs(d["value"] - per_step / (d["ms_per_step"] * 1e-3) / 1e6) / d["value"] < 1e-3
+
+
+# ---- round 2: the one line carries every BASELINE config, the strong-scaling block and the measured peaks ---------------
+R02 = os.path.join(ROOT, "profiles", "r02_bench_n1.json")
+R02_N2 = os.path.join(ROOT, "profiles", "r02_bench_n2.json")
+R02_REF = os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json")
+
+
+def _line(path):
+    return json.loads(open(path).read().strip().splitlines()[-1])
+
+
+def test_r02_line_carries_all_five_configs():
+    d = _line(R02)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "workloads", "strong", "peaks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["hits"]["all_planted_found_and_nothing_else"] is True and d["cpu_baseline"]["hits_equal_gpu"] is True
+    w = d["workloads"]
+    assert set(w) == {"c1", "c3", "c4", "c5btc", "c5eth"}
+    for name in ("c1", "c3", "c5btc", "c5eth"):
+        x = w[name]
+        assert x["value"] > 0 and x["e2e"]["value"] > 0 and x["hits"]["all_planted_found_and_nothing_else"] is True, name
+        assert 0 < x["roofline"]["frac"] < 1 and x["cpu_baseline"]["value"] > 0 and x["cpu_baseline"]["hits_equal_gpu"] in (True, None), name
+        assert x["value"] > 20 * x["cpu_baseline"]["value"]
+    c4 = w["c4"]
+    assert c4["planted"]["found"] is True and c4["unit"] == c4["cpu_baseline"]["unit"] == "M giant steps/s"      # like for like: giant steps/s on both sides
+    assert c4["value"] > 20 * c4["cpu_baseline"]["value"]
+    for cur in ("c5btc", "c5eth"):
+        s = d["strong"]["c5"][cur]
+        assert s["planted_found_and_nothing_else"] is True and s["keys"] == 1 << 37 and 0.9 < s["efficiency"] <= 1.001
+    assert d["strong"]["c4"]["planted"]["planted_found"] is True
+    for k in ("lop3", "imad", "imad_wide", "lop3_imad_mix", "dfma", "imad_wide_nocarry", "imad_wide_nocarry_plus_lop3"):
+        assert d["peaks"][k] > 1e12, k
+
+
+def test_r02_strong_scaling_on_two_gpus():
+    d1, d2 = _line(R02), _line(R02_N2)
+    assert d2["n_gpus"] == 2 and d2["hits"]["all_planted_found_and_nothing_else"] is True
+    assert 1.9 < d2["value"] / d1["value"] < 2.1                                   # weak scaling of the headline workload
+    for cur in ("c5btc", "c5eth"):
+        a, b = d1["strong"]["c5"][cur], d2["strong"]["c5"][cur]
+        assert b["planted_found_and_nothing_else"] is True and a["keys"] == b["keys"]
+        assert b["time_s"] < 0.55 * a["time_s"] and b["efficiency"] > 0.95          # the SAME range in half the time, clock around set-up + scan + gather
+    s1, s2 = d1["strong"]["c4"]["sweep"], d2["strong"]["c4"]["sweep"]
+    assert s1["giant_steps"] == s2["giant_steps"] and s2["time_s"] < 0.56 * s1["time_s"]
+    assert d2["strong"]["c4"]["planted"]["planted_found"] is True
+
+
+def test_r02_reference_arm_agrees_with_the_inline_cpu_baseline():
+    r, d = _line(R02_REF), _line(R02)
+    assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
+    assert abs(r["value"] - d["cpu_baseline"]["value"]) / d["cpu_baseline"]["value"] < 0.03
