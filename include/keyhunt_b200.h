@@ -46,6 +46,9 @@ const char *kh_last_error(kh_ctx *ctx);
  *  either way, the bloom image and table returned by kh_get_bloom / kh_get_table are unaffected),
  * "bsgs_prefilter" (default 1: kh_bsgs_build also fills an exact bitmap over the first bits of every baby point's X, up to
  *  3/4 of the free HBM, which answers most tier-1 probes with one memory access; found keys are identical),
+ * "bsgs_binned_build" (default 1: kh_bsgs_build bins the bloom / bitmap updates of tables with >= 2^26 baby steps by the
+ *  first bits of X so that they hit L2 instead of 21 random HBM read-modify-writes per baby step; 2 = always, 0 = never; the
+ *  tables are byte-identical either way),
  * "bsgs_base_check" (1 = kh_bsgs_search behaves like the reference SERVER's loop, which also reports a key equal to
  *  the base key of a 2N window, bsgsd.cpp:2544; 0 = keyhunt.cpp's thread_process_bsgs, the default) */
 int kh_set_option(kh_ctx *ctx, const char *name, int64_t value);
@@ -118,6 +121,10 @@ int kh_bsgs_describe(kh_ctx *ctx, kh_bsgs_desc *out);
 /* tier 1..3: bf bytes of one shard; tier 0: the bP table (m3 x 16-byte struct bsgs_xvalue, shard ignored) */
 int kh_bsgs_export(kh_ctx *ctx, int tier, int shard, void *dst, uint64_t cap_bytes);
 int kh_bsgs_import(kh_ctx *ctx, int tier, int shard, const void *src, uint64_t len_bytes);
+/* order-independent 64-bit digest, computed on the device, of the bP table (tier 0), of all 256 shards of bloom tier 1..3, or of
+ * the baby-point prefix bitmap (tier 4; "bsgs_prefilter").  Two builds hold the same bytes iff (up to 2^-64) the digests agree: the
+ * way to compare tables that are too big to export (7.7 GB tier 1 and a 64 GB bitmap at -k 512). */
+int kh_bsgs_digest(kh_ctx *ctx, int tier, uint64_t *out);
 /* sequential search (-B sequential) of [start, end) for one public key, in windows of 2n keys like
  * thread_process_bsgs; *found = 1 and the key when found. */
 int kh_bsgs_search(kh_ctx *ctx, const uint8_t pub_xy_be[64], const uint8_t start_be[32], const uint8_t end_be[32],

@@ -30,7 +30,7 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 EXPORTS = ["kh_create", "kh_destroy", "kh_last_error", "kh_set_option", "kh_bloom_params", "kh_set_targets",
            "kh_get_bloom", "kh_get_table", "kh_scan", "kh_poll_hits", "kh_derive", "kh_bsgs_build",
-           "kh_bsgs_describe", "kh_bsgs_export", "kh_bsgs_import", "kh_bsgs_search", "kh_get_stats",
+           "kh_bsgs_describe", "kh_bsgs_export", "kh_bsgs_import", "kh_bsgs_digest", "kh_bsgs_search", "kh_get_stats",
            "kh_device_info", "kh_int_peak", "kh_set_vanity", "kh_pipe_peak", "kh_hash_peak", "kh_selftest_fe"]
 
 # kh_selftest_fe ops (include/keyhunt_b200.h)
@@ -143,6 +143,8 @@ def load_library(path=None):
         L.kh_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.kh_hash_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
         L.kh_selftest_fe.argtypes = [vp, C.c_int, u8p, u8p, u64, vp]
+    if path is None or hasattr(L, "kh_bsgs_digest"):
+        L.kh_bsgs_digest.argtypes = [vp, C.c_int, C.POINTER(u64)]
     for name in EXPORTS:
         if name not in ("kh_destroy", "kh_last_error") and (path is None or hasattr(L, name)):
             getattr(L, name).restype = C.c_int
@@ -279,6 +281,12 @@ class KeyHunt:
         buf = C.create_string_buffer(max(1, size))
         self._ck(self._lib.kh_bsgs_export(self._h, tier, shard, buf, size))
         return buf.raw[:size]
+
+    def bsgs_digest(self, tier):
+        """device-side digest of the bP table (0), a whole bloom tier (1..3) or the baby-point prefix bitmap (4)"""
+        out = C.c_uint64()
+        self._ck(self._lib.kh_bsgs_digest(self._h, tier, C.byref(out)))
+        return out.value
 
     def bsgs_import(self, tier, shard, data):
         self._ck(self._lib.kh_bsgs_import(self._h, tier, shard, data, len(data)))

@@ -254,6 +254,21 @@ KH_HD bool bsgs_pre_test(const uint32_t *pre, uint32_t k, const fe &x) {
   return (kh_ld_probe32(pre + (idx >> 5)) >> (uint32_t)(idx & 31)) & 1u;
 }
 
+// Binned table build.  A baby point sets 20 bits of ONE tier-1 shard (shard = first byte of X, ~30 MB at -k 512) and one bit of
+// the prefix bitmap (indexed by the first pre_k bits of X).  Done directly that is 21 random read-modify-writes over 72 GB per
+// point (0.99 G baby steps/s, bound by DRAM transactions).  Binned: the walk only appends (a, b, low index bits) of each
+// point to the bucket of the first KH_BABY_BUCKET_BITS bits of its X; a second kernel then applies the buckets in order, so
+// that at any moment the SMs work on a few consecutive buckets = ONE bloom shard (L2-resident) and a few 16 MB bitmap regions.
+// The OR-ed image is the same whatever the order (byte-identical files, tests/test_gpu_bsgs.py).
+#define KH_BABY_BUCKET_BITS 12
+struct BabyBins {
+  uint64_t *a, *b;        // XXH64(X, seed), XXH64(X, a)
+  uint32_t *lo;           // bitmap index below the bucket bits
+  uint32_t *count;        // records per bucket (may exceed cap: the excess took the direct path)
+  uint32_t cap;           // records a bucket holds; 0 = binning off (everything direct)
+  uint32_t pad;
+};
+
 // baby steps: point p = batch*1024 + idx is (p+1)*G            (thread_bPload keyhunt.cpp:5394-5443)
 struct BabyEmit {
   static constexpr bool NEED_Y = false;
@@ -265,7 +280,9 @@ struct BabyEmit {
     point(xb, dummy, batch, ib);
   }
   const BsgsTables &bt;
-  KH_HDM explicit BabyEmit(const BsgsTables &b) : bt(b) {}
+  BabyBins bins;
+  KH_HDM explicit BabyEmit(const BsgsTables &b) : bt(b) { bins.a = bins.b = nullptr; bins.lo = nullptr; bins.count = nullptr; bins.cap = 0; bins.pad = 0; }
+  KH_HDM BabyEmit(const BsgsTables &b, const BabyBins &bn) : bt(b), bins(bn) {}
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
     const uint64_t p = batch * KH_GRP + idx;
     if (p >= bt.m) return;
@@ -286,6 +303,16 @@ struct BabyEmit {
       bloom_set(bt.tier[2], shard, a, b);
     }
     if (p < bt.m2) bloom_set(bt.tier[1], shard, a, b);
+    if (bins.cap) {                                       // binned: append, the apply kernel sets the bits
+      const uint32_t bucket = x.v[7] >> (32 - KH_BABY_BUCKET_BITS);
+      const uint32_t slot = kh_atomic_inc(bins.count + bucket);
+      if (slot < bins.cap) {
+        const uint64_t at = (uint64_t)bucket * bins.cap + slot;
+        bins.a[at] = a; bins.b[at] = b;
+        bins.lo[at] = bt.pre_k ? (uint32_t)(bsgs_pre_index(x, bt.pre_k) & ((1ull << (bt.pre_k - KH_BABY_BUCKET_BITS)) - 1)) : 0u;
+        return;
+      }
+    }
     bloom_set(bt.tier[0], shard, a, b);
     if (bt.pre_k) {
       const uint64_t idx = bsgs_pre_index(x, bt.pre_k);

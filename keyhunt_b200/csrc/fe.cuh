@@ -111,6 +111,23 @@ KH_HD void kh_mad_row(uint32_t *acc, uint32_t a0, uint32_t a2, uint32_t a4, uint
   acc[8] += (uint32_t)c;
 #endif
 }
+// A wide multiply-add that neither takes nor produces a carry (IMAD.WIDE.U32 with RZ as addend) costs the multiplier about half of
+// a link of a carry chain (IMAD.WIDE.U32.X: 13.1 against 7.25 T/s, kh_pipe_peak), and a row that lands on accumulators that are still
+// zero needs no carries at all: its four products occupy four disjoint 64-bit lanes.  KH_PLAIN_HEAD = 1 writes those rows as
+// plain products (8 of the 64 products of fe_mul_wide, 4 of the 8 of fe_reduce_wide, 7 of the 28 off-diagonal ones of fe_sqr_wide).
+#ifndef KH_PLAIN_HEAD
+#define KH_PLAIN_HEAD 1
+#endif
+// acc[0..2N-1] = x[k]*y[k] as N adjacent 64-bit lanes (acc was zero)
+template <int N>
+KH_HD void kh_mul_lanes(uint32_t *acc, const uint32_t *x, const uint32_t *y) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const uint64_t p = (uint64_t)x[k] * y[k];
+    acc[2 * k] = (uint32_t)p;
+    acc[2 * k + 1] = (uint32_t)(p >> 32);
+  }
+}
 // acc[0..2N-1] += x[k]*y[k] as N adjacent 64-bit lanes (k < N <= 4); the carry-out is added into acc[2N]
 template <int N>
 KH_HD void kh_mad_chain(uint32_t *acc, const uint32_t *x, const uint32_t *y) {
@@ -274,8 +291,14 @@ KH_HD void fe_mul_wide(uint32_t r[16], const fe &a, const fe &b) {
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
     // row i (even): even j -> even column -> e[i+j] ; odd j -> odd column -> o[i+j-1]
-    kh_mad_row(e + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-    kh_mad_row(o + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    if (KH_PLAIN_HEAD && i == 0) {   // both accumulators are still zero: eight carry-free products
+      const uint32_t xe[4] = {a.v[0], a.v[2], a.v[4], a.v[6]}, xo[4] = {a.v[1], a.v[3], a.v[5], a.v[7]}, y[4] = {b.v[0], b.v[0], b.v[0], b.v[0]};
+      kh_mul_lanes<4>(e, xe, y);
+      kh_mul_lanes<4>(o, xo, y);
+    } else {
+      kh_mad_row(e + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      kh_mad_row(o + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    }
     // row i+1 (odd): odd j -> even column -> e[i+1+j] ; even j -> odd column -> o[i+j]
     kh_mad_row(e + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
     kh_mad_row(o + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
@@ -291,6 +314,10 @@ KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
   for (int i = 0; i < 8; i++) { e[i] = w[i]; o[i] = 0; }
   e[8] = 0; o[8] = 0;
   kh_mad_row(e, w[8], w[10], w[12], w[14], 977u);  // hi limbs 0,2,4,6 -> columns 0,2,4,6
+  if (KH_PLAIN_HEAD) {                             // o is zero: four carry-free products
+    const uint32_t xo[4] = {w[9], w[11], w[13], w[15]}, y[4] = {977u, 977u, 977u, 977u};
+    kh_mul_lanes<4>(o, xo, y);
+  } else
   kh_mad_row(o, w[9], w[11], w[13], w[15], 977u);  // hi limbs 1,3,5,7 -> columns 1,3,5,7 (o[k] <-> limb k+1)
   uint32_t t[8], top0, top1;
   // limbs 1..8 : e[1..8] + o[0..7] ; limb 9 : o[8] + carry
@@ -326,8 +353,13 @@ KH_HD void fe_sqr_wide(uint32_t r[16], const fe &a) {
   for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
   const uint32_t *v = a.v;
   // row i: a_i * a_j for j > i ; column i+j odd -> o[i+j-1], even -> e[i+j]
+  if (KH_PLAIN_HEAD) {   // the first chain of each accumulator lands on zeros: seven carry-free products
+    { const uint32_t x[4] = {v[0], v[0], v[0], v[0]}, y[4] = {v[1], v[3], v[5], v[7]}; kh_mul_lanes<4>(o + 0, x, y); }
+    { const uint32_t x[3] = {v[0], v[0], v[0]}, y[3] = {v[2], v[4], v[6]}; kh_mul_lanes<3>(e + 2, x, y); }
+  } else {
   { const uint32_t x[4] = {v[0], v[0], v[0], v[0]}, y[4] = {v[1], v[3], v[5], v[7]}; kh_mad_chain<4>(o + 0, x, y); }
   { const uint32_t x[3] = {v[0], v[0], v[0]}, y[3] = {v[2], v[4], v[6]}; kh_mad_chain<3>(e + 2, x, y); }
+  }
   { const uint32_t x[3] = {v[1], v[1], v[1]}, y[3] = {v[2], v[4], v[6]}; kh_mad_chain<3>(o + 2, x, y); }
   { const uint32_t x[3] = {v[1], v[1], v[1]}, y[3] = {v[3], v[5], v[7]}; kh_mad_chain<3>(e + 4, x, y); }
   { const uint32_t x[3] = {v[2], v[2], v[2]}, y[3] = {v[3], v[5], v[7]}; kh_mad_chain<3>(o + 4, x, y); }

@@ -36,13 +36,30 @@ __device__ __forceinline__ void kh_stage_table_b(uint32_t *smem, const uint32_t 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(KH_BLOCK, KH_BABY_MINBLOCKS) kh_baby_kernel(WalkParams wp, BsgsTables bt) {
+__global__ void __launch_bounds__(KH_BLOCK, KH_BABY_MINBLOCKS) kh_baby_kernel(WalkParams wp, BsgsTables bt, BabyBins bins) {
   extern __shared__ __align__(16) uint32_t kh_smem_tab[];
   kh_stage_table_b(kh_smem_tab, wp.gtab);
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= wp.T) return;
-  BabyEmit emit(bt);
+  BabyEmit emit(bt, bins);
   walk_batches(wp, kh_smem_tab, t, emit);
+}
+
+// applies the binned records (emit.cuh BabyBins): CTAs are dispatched in index order = bucket order, so the resident CTAs
+// work on a few consecutive buckets: one tier-1 shard and a few 16 MB regions of the prefix bitmap, all in L2
+__global__ void __launch_bounds__(256) kh_baby_apply(BabyBins bins, BsgsTables bt, uint32_t blocks_per_bucket) {
+  const uint32_t bucket = blockIdx.x / blocks_per_bucket;
+  const uint32_t slot = (blockIdx.x % blocks_per_bucket) * 256u + threadIdx.x;
+  uint32_t n = bins.count[bucket];
+  if (n > bins.cap) n = bins.cap;
+  if (slot >= n) return;
+  const uint64_t at = (uint64_t)bucket * bins.cap + slot;
+  const uint64_t a = bins.a[at], b = bins.b[at];
+  bloom_set(bt.tier[0], bucket >> (KH_BABY_BUCKET_BITS - 8), a, b);
+  if (bt.pre_k) {
+    const uint64_t idx = ((uint64_t)bucket << (bt.pre_k - KH_BABY_BUCKET_BITS)) | bins.lo[at];
+    atomicOr(bt.pre + (idx >> 5), 1u << (uint32_t)(idx & 31));
+  }
 }
 
 __global__ void __launch_bounds__(KH_BLOCK, KH_GIANT_MINBLOCKS) kh_giant_kernel(WalkParams wp, GiantParams gp) {
@@ -86,6 +103,22 @@ __global__ void kh_diff_kernel(const uint8_t *a, const uint8_t *b, uint64_t n, u
   bool diff = false;
   for (uint64_t i = i0; i < n && i < i0 + 16; i++) diff |= (a[i] != b[i]);
   if (diff) atomicOr(flag, 1u);
+}
+
+// order-independent digest of a byte range (kh_bsgs_digest): sum over its 4-byte words of mix(word, position) mod 2^64.
+// Lets a test compare two builds of tables that are too big to bring to the host (7.7 GB tier 1, 64 GB prefix bitmap).
+__global__ void __launch_bounds__(256) kh_digest_kernel(const uint32_t *w, uint64_t n_words, uint64_t salt, unsigned long long *out) {
+  uint64_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = w[i];
+    if (v) {
+      uint64_t h = (i + salt) * 0x9E3779B97F4A7C15ull + v;
+      h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+      acc += h;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
 }
 
 // ---- AMP tables: entry i (<32) = -(2i+1)*m2*G, entry 32+i = -(2i+1)*m3*G ------------------------------
@@ -318,14 +351,45 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
   WalkParams wp;
   wp.gtab = c->d_gtab; wp.centers = c->d_centers; wp.scratch = c->d_scratch;
   wp.T = T; wp.n_batches = n_batches; wp.steps = (uint32_t)c->steps_per_launch; wp.pad = 0;
+  // binned build (emit.cuh BabyBins) for tables that do not fit L2 anyway: one step of the walk per launch, then its buckets
+  // are applied.  The record buffers (20 B per point of one step, ~12.7 GB for 606,208 walkers) live only during the build.
+  BabyBins bins;
+  memset(&bins, 0, sizeof(bins));
+  void *bin_mem = nullptr;
+  uint32_t blocks_per_bucket = 0;
+  const uint32_t n_buckets = 1u << KH_BABY_BUCKET_BITS;
+  if (c->bsgs_binned_build && (c->bsgs_binned_build == 2 || d.m >= (1ull << 26)) && (c->bsgs_pre_k == 0 || (c->bsgs_pre_k >= KH_BABY_BUCKET_BITS + 8 && c->bsgs_pre_k - KH_BABY_BUCKET_BITS <= 32))) {
+    const uint64_t per_launch = std::min<uint64_t>(T * (uint64_t)KH_GRP, d.m);
+    const uint64_t avg = per_launch / n_buckets;
+    const uint64_t cap = avg + avg / 32 + 4096;                     // ~6 sigma above the mean for uniformly distributed X
+    const size_t recs = (size_t)cap * n_buckets;
+    if (cap < (1ull << 31) && cudaMalloc(&bin_mem, recs * 20 + n_buckets * sizeof(uint32_t) + 64) == cudaSuccess) {
+      bins.a = static_cast<uint64_t *>(bin_mem);
+      bins.b = bins.a + recs;
+      bins.lo = reinterpret_cast<uint32_t *>(bins.b + recs);
+      bins.count = bins.lo + recs;
+      bins.cap = (uint32_t)cap;
+      blocks_per_bucket = (uint32_t)((cap + 255) / 256);
+      wp.steps = 1;
+    } else {
+      cudaGetLastError();
+      bin_mem = nullptr;
+    }
+  }
   kh_time_begin(c);
   uint64_t launches = 0;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
     wp.batch_base = base;
-    kh_baby_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, bt);
+    if (bins.cap) cudaMemsetAsync(bins.count, 0, n_buckets * sizeof(uint32_t), c->stream);
+    kh_baby_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, bt, bins);
     launches++;
+    if (bins.cap) {
+      kh_baby_apply<<<n_buckets * blocks_per_bucket, 256, 0, c->stream>>>(bins, bt, blocks_per_bucket);
+      launches++;
+    }
   }
   c->stats.walk_ms += kh_time_end(c);
+  if (bin_mem) cudaFree(bin_mem);
   c->stats.walk_launches += launches;
   c->stats.points += d.m;
   c->stats.walker_threads = T;
@@ -374,6 +438,28 @@ int kh_bsgs_export(kh_ctx *c, int tier, int shard, void *dst, uint64_t cap) {
   if (cap < len) return kh_fail(c, KH_EINVAL, "buffer too small (%llu < %llu)", (unsigned long long)cap, (unsigned long long)len);
   KH_CUDA(c, cudaMemcpyAsync(dst, p, len, cudaMemcpyDeviceToHost, c->stream));
   KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KH_OK;
+}
+
+int kh_bsgs_digest(kh_ctx *c, int tier, uint64_t *out) {
+  if (!c || !out) return KH_EINVAL;
+  cudaSetDevice(c->device);
+  if (!c->have_bsgs) return kh_fail(c, KH_ESTATE, "kh_bsgs_build has not run");
+  const uint8_t *p; uint64_t len;
+  if (tier == 0) { p = reinterpret_cast<const uint8_t *>(c->d_bptable); len = c->bsgs.m3 * sizeof(BpEntry); }
+  else if (tier >= 1 && tier <= 3) { p = c->d_tier[tier - 1]; len = (uint64_t)c->tier_stride[tier - 1] * 256; }
+  else if (tier == 4) { p = reinterpret_cast<const uint8_t *>(c->d_bsgs_pre); len = c->bsgs_pre_k ? (1ull << (c->bsgs_pre_k - 3)) : 0; }
+  else return kh_fail(c, KH_EINVAL, "bad tier");
+  unsigned long long *d_out = nullptr;
+  KH_CUDA(c, cudaMalloc(&d_out, sizeof(unsigned long long)));
+  cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), c->stream);
+  if (len) kh_digest_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(p), len / 4, (uint64_t)tier << 56, d_out);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_out);
+  KH_CUDA(c, cudaGetLastError());
+  *out = (uint64_t)h + len;       // the length takes part: an absent bitmap (len 0) differs from an empty one
   return KH_OK;
 }
 

@@ -32,6 +32,7 @@ struct kh_ctx {
   int prefilter = 1;               // exact prefix bitmap in front of the bloom for target sets of <= 65,536 records
   int bsgs_prefilter = 1;          // build the baby-point prefix bitmap when HBM allows (kh_bsgs_build)
   int bsgs_base_check = 0;         // server variant of the BSGS search (bsgsd.cpp:2544)
+  int bsgs_binned_build = 1;       // kh_bsgs_build bins the bloom / bitmap updates by X prefix so that they hit L2 (emit.cuh BabyBins)
 
   // walk state
   uint64_t T_alloc = 0;            // walker threads the buffers are sized for

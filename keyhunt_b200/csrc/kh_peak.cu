@@ -131,6 +131,20 @@ __global__ void __launch_bounds__(256) kh_pipe_kernel(uint32_t *out, uint32_t se
       } else if (KIND == 8) {   // IMAD.WIDE.U32 without carries + LOP3: do the FMA-heavy and the ALU pipe overlap when no carry is involved?
         asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(f_as_u[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 9) {   // "head" form: a wide multiply-add that produces a carry but takes none, its carry collected by one IADD3.X
+        uint32_t lo = (uint32_t)w[i], hi = (uint32_t)(w[i] >> 32);
+        asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(f_as_u[i]) : "r"(a[i]), "r"(b[i]));
+        w[i] = ((uint64_t)hi << 32) | lo;
+      } else if (KIND == 10) {  // carry-free wide multiply-add + one plain IADD3 (the comparison for KIND 9)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(f_as_u[i]) : "r"(b[i]), "r"(it));
+      } else if (KIND == 11) {  // two-link chain: head + one IMAD.WIDE.U32.X + the IADD3.X that collects the carry (2 wide ops + 1 ALU op)
+        if (i < 8) {
+          uint32_t lo = (uint32_t)w[2 * i], hi = (uint32_t)(w[2 * i] >> 32), lo2 = (uint32_t)w[2 * i + 1], hi2 = (uint32_t)(w[2 * i + 1] >> 32);
+          asm volatile("mad.lo.cc.u32 %0, %5, %6, %0;\n\tmadc.hi.cc.u32 %1, %5, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %7, %2;\n\tmadc.hi.cc.u32 %3, %5, %7, %3;\n\taddc.u32 %4, %4, 0;"
+                       : "+r"(lo), "+r"(hi), "+r"(lo2), "+r"(hi2), "+r"(f_as_u[i]) : "r"(a[i]), "r"(b[i]), "r"(b[i + 8]));
+          w[2 * i] = ((uint64_t)hi << 32) | lo; w[2 * i + 1] = ((uint64_t)hi2 << 32) | lo2;
+        }
       } else if (KIND == 7) {
         // the x-only walk's own mix: per point 224 wide multiply-adds in carry chains and ~470 ALU-pipe ops (ncu), i.e.
         // 16 IMAD.WIDE.U32.X + 34 ALU ops per trip here (half LOP3, half carry-free IADD3)
@@ -181,9 +195,12 @@ extern "C" int kh_pipe_peak(kh_ctx *c, double out[16]) {
   out[6] = run_pipe<6>(c, d_out, 1);
   out[7] = run_pipe<7>(c, d_out, 1);
   out[8] = run_pipe<8>(c, d_out, 2);   // IMAD.WIDE.U32 (no carry) + LOP3 together, total ops/s
-  for (int i = 9; i < 16; i++) out[i] = 0;   // trips x 16 per second = IMAD.WIDE.U32.X per second inside the walk's mix (16 per trip)
+  out[9] = run_pipe<9>(c, d_out, 2);    // head-form IMAD.WIDE (carry out only) + IADD3.X, total ops/s
+  out[10] = run_pipe<10>(c, d_out, 2);  // carry-free IMAD.WIDE + IADD3, total ops/s
+  out[11] = run_pipe<11>(c, d_out, 1) * (24.0 / 16.0);   // 8 x (head + .X + IADD3.X) per trip = 24 ops, total ops/s
+  for (int i = 12; i < 16; i++) out[i] = 0;   // trips x 16 per second = IMAD.WIDE.U32.X per second inside the walk's mix (16 per trip)
   cudaFree(d_out);
-  c->stats.other_launches += 36;
+  c->stats.other_launches += 48;
   KH_CUDA(c, cudaGetLastError());
   return KH_OK;
 }

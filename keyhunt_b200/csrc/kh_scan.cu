@@ -255,6 +255,9 @@ int kh_set_option(kh_ctx *c, const char *name, int64_t value) {
     c->prefilter = value ? 1 : 0;
   } else if (!strcmp(name, "bsgs_prefilter")) {    // baby-point prefix bitmap in front of the tier-1 bloom (next kh_bsgs_build)
     c->bsgs_prefilter = value ? 1 : 0;
+  } else if (!strcmp(name, "bsgs_binned_build")) { // 0 = every baby step sets its bits directly (A/B, and the small-table path)
+    if (value < 0 || value > 2) return kh_fail(c, KH_EINVAL, "bsgs_binned_build is 0, 1 (tables of 2^26 baby steps and more) or 2 (always)");
+    c->bsgs_binned_build = (int)value;
   } else if (!strcmp(name, "bsgs_base_check")) {   // the reference SERVER's search loop (bsgsd.cpp:2544)
     c->bsgs_base_check = value ? 1 : 0;
   } else if (!strcmp(name, "hit_capacity")) {

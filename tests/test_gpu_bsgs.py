@@ -1,13 +1,17 @@
 """GPU parity tests for the BSGS path (through the C ABI) against the CPU oracle: byte-identical
 3-tier bloom shards and bP table, identical found keys."""
 import hashlib
+import json
+import os
 import random
+import time
 
 import pytest
 
 from _oracle import N_ORDER, P_FIELD
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _canon_table(raw):
@@ -34,6 +38,23 @@ def test_bsgs_build_is_byte_identical(kh, oracle, n, k):
         assert _canon_table(got) == [(got[i:i + 6], int.from_bytes(got[i + 8:i + 16], "little")) for i in range(0, len(got), 16)]
     finally:
         oracle.bsgs_free(b)
+
+
+@pytest.mark.parametrize("n,k", [(1 << 20, 1), (1 << 24, 4), (1 << 26, 3)])
+def test_bsgs_binned_build_equals_direct(kh, n, k):
+    """option "bsgs_binned_build": baby points binned by the first 12 bits of X and applied bucket by bucket (the way big tables
+    are built) give the same bytes as setting every bit directly: digests of every tier, of the bP table and of the prefix bitmap,
+    and the raw bytes of sampled shards."""
+    seen = {}
+    try:
+        for mode in (0, 2):
+            kh.set_option("bsgs_binned_build", mode)
+            kh.bsgs_build(n, k)
+            seen[mode] = [kh.bsgs_digest(t) for t in range(5)] + [hashlib.sha256(kh.bsgs_export(1, s)).hexdigest() for s in (0, 17, 255)]
+    finally:
+        kh.set_option("bsgs_binned_build", 1)
+    assert seen[0] == seen[2]
+    assert len(set(seen[0][:5])) == 5
 
 
 def test_bsgs_search_finds_planted_keys(kh, oracle):
@@ -111,6 +132,29 @@ def test_c4_full_size_properties(kh, oracle):
         assert kh.bsgs_search(oracle.pubkey(key), lo, hi) == key
     st = kh.stats()
     assert st["tier1_positives"] > 0
+    # the tables above were built binned (the default for >= 2^26 baby steps); a direct build holds the same bytes in all
+    # 7.7 GB of tier 1 and all 64 GB of the prefix bitmap (device-side digests), and takes several times longer
+    binned = [kh.bsgs_digest(t) for t in range(5)]
+    kh.stats(reset=True)
+    t0 = time.time(); kh.bsgs_build(1 << 44, 512); t_binned = time.time() - t0
+    ms_binned = kh.stats(reset=True)["walk_ms"]
+    assert [kh.bsgs_digest(t) for t in range(5)] == binned
+    try:
+        kh.set_option("bsgs_binned_build", 0)
+        t0 = time.time(); kh.bsgs_build(1 << 44, 512); t_direct = time.time() - t0
+        ms_direct = kh.stats(reset=True)["walk_ms"]
+        assert [kh.bsgs_digest(t) for t in range(5)] == binned
+    finally:
+        kh.set_option("bsgs_binned_build", 1)
+    try:        # evidence for profiles/ (the GPU box merges gpurun_out/ back)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump({"what": "kh_bsgs_build(n = 2^44, k = 512): 2^31 baby steps into the 7.7 GB tier-1 bloom + 64 GB prefix bitmap, seconds",
+                   "binned_wall_s": t_binned, "direct_wall_s": t_direct, "binned_walk_ms": ms_binned, "direct_walk_ms": ms_direct,
+                   "baby_steps_per_s_binned": d.m / (ms_binned * 1e-3), "baby_steps_per_s_direct": d.m / (ms_direct * 1e-3),
+                   "digests_equal": True},
+                  open(os.path.join(ROOT, "gpurun_out", "bsgs_build_binned.json"), "w"))
+    except OSError:
+        pass
 
 
 def test_bsgs_server_variant_base_check(kh, oracle):
