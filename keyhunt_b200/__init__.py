@@ -309,7 +309,8 @@ class KeyHunt:
         """more measured pipe rates (thread-ops/s, whole chip): the evidence behind the choice of multiplier"""
         arr = (C.c_double * 16)()
         self._ck(self._lib.kh_pipe_peak(self._h, arr))
-        return dict(zip(["imad_wide_nocarry", "imad_hi", "dfma", "dadd", "dfma_plus_imad_wide", "imad_wide_plus_iadd3", "ffma", "imad_wide_in_walk_mix", "imad_wide_nocarry_plus_lop3"],
+        return dict(zip(["imad_wide_nocarry", "imad_hi", "dfma", "dadd", "dfma_plus_imad_wide", "imad_wide_plus_iadd3", "ffma", "imad_wide_in_walk_mix", "imad_wide_nocarry_plus_lop3",
+                         "imad_wide_carryout_plus_iadd3x", "imad_wide_nocarry_plus_iadd3", "imad_wide_2link_chain_plus_iadd3x"],
                         [float(x) for x in arr]))
 
     def hash_peak(self, blocks_per_sm=2):

@@ -286,6 +286,10 @@ struct BabyEmit {
   KH_HDM void point(const fe &x, const fe &, uint64_t batch, uint32_t idx) {
     const uint64_t p = batch * KH_GRP + idx;
     if (p >= bt.m) return;
+    // binned: claim the record slot first — the counter's round trip to L2 is hidden behind the two XXH64 below
+    const uint32_t bucket = x.v[7] >> (32 - KH_BABY_BUCKET_BITS);
+    uint32_t slot = 0xFFFFFFFFu;
+    if (bins.cap) slot = kh_atomic_inc(bins.count + bucket);
     uint32_t w[8];
     fe_to_le_words(w, x);
     const uint64_t a = xxh64_32(w, KH_BLOOM_SEED);
@@ -303,15 +307,11 @@ struct BabyEmit {
       bloom_set(bt.tier[2], shard, a, b);
     }
     if (p < bt.m2) bloom_set(bt.tier[1], shard, a, b);
-    if (bins.cap) {                                       // binned: append, the apply kernel sets the bits
-      const uint32_t bucket = x.v[7] >> (32 - KH_BABY_BUCKET_BITS);
-      const uint32_t slot = kh_atomic_inc(bins.count + bucket);
-      if (slot < bins.cap) {
-        const uint64_t at = (uint64_t)bucket * bins.cap + slot;
-        bins.a[at] = a; bins.b[at] = b;
-        bins.lo[at] = bt.pre_k ? (uint32_t)(bsgs_pre_index(x, bt.pre_k) & ((1ull << (bt.pre_k - KH_BABY_BUCKET_BITS)) - 1)) : 0u;
-        return;
-      }
+    if (slot < bins.cap) {                                // binned: append, the apply kernel sets the bits (cap = 0: never)
+      const uint64_t at = (uint64_t)bucket * bins.cap + slot;
+      bins.a[at] = a; bins.b[at] = b;
+      bins.lo[at] = bt.pre_k ? (uint32_t)(bsgs_pre_index(x, bt.pre_k) & ((1ull << (bt.pre_k - KH_BABY_BUCKET_BITS)) - 1)) : 0u;
+      return;
     }
     bloom_set(bt.tier[0], shard, a, b);
     if (bt.pre_k) {

@@ -45,20 +45,42 @@ __global__ void __launch_bounds__(KH_BLOCK, KH_BABY_MINBLOCKS) kh_baby_kernel(Wa
   walk_batches(wp, kh_smem_tab, t, emit);
 }
 
-// applies the binned records (emit.cuh BabyBins): CTAs are dispatched in index order = bucket order, so the resident CTAs
-// work on a few consecutive buckets: one tier-1 shard and a few 16 MB regions of the prefix bitmap, all in L2
-__global__ void __launch_bounds__(256) kh_baby_apply(BabyBins bins, BsgsTables bt, uint32_t blocks_per_bucket) {
-  const uint32_t bucket = blockIdx.x / blocks_per_bucket;
-  const uint32_t slot = (blockIdx.x % blocks_per_bucket) * 256u + threadIdx.x;
+// applies the binned records (emit.cuh BabyBins).  CTAs are dispatched in index order = (shard, pass, bucket of the shard, block),
+// so the resident CTAs work on ONE slice of ONE tier-1 shard (a pass covers the bit positions [pass, pass+1) * pass_bits of the
+// shard: <= 48 MB, L2-resident; a shard of -k 512 is one slice, one of -k 4096 six) and on a few 16 MB regions of the prefix bitmap
+__global__ void __launch_bounds__(256) kh_baby_apply(BabyBins bins, BsgsTables bt, uint32_t blocks_per_bucket, uint32_t n_pass, uint64_t pass_bits) {
+  constexpr uint32_t BPS = 1u << (KH_BABY_BUCKET_BITS - 8);      // buckets per shard
+  uint32_t idx = blockIdx.x;
+  const uint32_t blk = idx % blocks_per_bucket; idx /= blocks_per_bucket;
+  const uint32_t bis = idx % BPS; idx /= BPS;
+  const uint32_t pass = idx % n_pass, shard = idx / n_pass;
+  const uint32_t bucket = shard * BPS + bis;
+  const uint32_t slot = blk * 256u + threadIdx.x;
   uint32_t n = bins.count[bucket];
   if (n > bins.cap) n = bins.cap;
   if (slot >= n) return;
   const uint64_t at = (uint64_t)bucket * bins.cap + slot;
   const uint64_t a = bins.a[at], b = bins.b[at];
-  bloom_set(bt.tier[0], bucket >> (KH_BABY_BUCKET_BITS - 8), a, b);
-  if (bt.pre_k) {
-    const uint64_t idx = ((uint64_t)bucket << (bt.pre_k - KH_BABY_BUCKET_BITS)) | bins.lo[at];
-    atomicOr(bt.pre + (idx >> 5), 1u << (uint32_t)(idx & 31));
+  if (n_pass == 1) {
+    bloom_set(bt.tier[0], shard, a, b);
+  } else {
+    const BloomDev &bl = bt.tier[0];
+    uint8_t *bf = bl.bf + (uint64_t)shard * bl.stride;
+    const uint64_t lo = (uint64_t)pass * pass_bits;
+    uint64_t x = a;
+#pragma unroll 1
+    for (uint32_t i = 0; i < bl.hashes; i++) {
+      const uint64_t r = bloom_mod(x, bl.bits, bl.magic);
+      if (r - lo < pass_bits) {
+        const uint64_t byte = r >> 3;
+        atomicOr(reinterpret_cast<uint32_t *>(bf + (byte & ~3ULL)), 1u << (8u * (uint32_t)(byte & 3) + (uint32_t)(r & 7)));
+      }
+      x += b;
+    }
+  }
+  if (bt.pre_k && pass == 0) {
+    const uint64_t idx2 = ((uint64_t)bucket << (bt.pre_k - KH_BABY_BUCKET_BITS)) | bins.lo[at];
+    atomicOr(bt.pre + (idx2 >> 5), 1u << (uint32_t)(idx2 & 31));
   }
 }
 
@@ -358,6 +380,13 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
   void *bin_mem = nullptr;
   uint32_t blocks_per_bucket = 0;
   const uint32_t n_buckets = 1u << KH_BABY_BUCKET_BITS;
+  // a tier-1 shard is applied in slices of <= 48 MB so that the slice being written stays in L2 (KH_BABY_SLICE_KB: tests, experiments)
+  uint64_t slice_bytes = 48ull << 20;
+  if (const char *e = getenv("KH_BABY_SLICE_KB")) { const long v = atol(e); if (v >= 1) slice_bytes = (uint64_t)v << 10; }
+  uint32_t n_pass = (uint32_t)((d.tier[0].bytes + slice_bytes - 1) / slice_bytes);
+  if (n_pass < 1) n_pass = 1;
+  if (n_pass > 64) n_pass = 64;
+
   if (c->bsgs_binned_build && (c->bsgs_binned_build == 2 || d.m >= (1ull << 26)) && (c->bsgs_pre_k == 0 || (c->bsgs_pre_k >= KH_BABY_BUCKET_BITS + 8 && c->bsgs_pre_k - KH_BABY_BUCKET_BITS <= 32))) {
     const uint64_t per_launch = std::min<uint64_t>(T * (uint64_t)KH_GRP, d.m);
     const uint64_t avg = per_launch / n_buckets;
@@ -370,12 +399,14 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
       bins.count = bins.lo + recs;
       bins.cap = (uint32_t)cap;
       blocks_per_bucket = (uint32_t)((cap + 255) / 256);
+      while (n_pass > 1 && (uint64_t)n_buckets * blocks_per_bucket * n_pass >= (1ull << 31)) n_pass--;   // one grid
       wp.steps = 1;
     } else {
       cudaGetLastError();
       bin_mem = nullptr;
     }
   }
+  const uint64_t pass_bits = (d.tier[0].bits + n_pass - 1) / n_pass;
   kh_time_begin(c);
   uint64_t launches = 0;
   for (uint64_t base = 0; base < n_batches; base += (uint64_t)wp.steps * T) {
@@ -384,7 +415,7 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
     kh_baby_kernel<<<(unsigned)(T / KH_BLOCK), KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, bt, bins);
     launches++;
     if (bins.cap) {
-      kh_baby_apply<<<n_buckets * blocks_per_bucket, 256, 0, c->stream>>>(bins, bt, blocks_per_bucket);
+      kh_baby_apply<<<n_buckets * blocks_per_bucket * n_pass, 256, 0, c->stream>>>(bins, bt, blocks_per_bucket, n_pass, pass_bits);
       launches++;
     }
   }

@@ -37,6 +37,7 @@ struct kh_ctx {
   // walk state
   uint64_t T_alloc = 0;            // walker threads the buffers are sized for
   uint32_t *d_gtab = nullptr;      // KH_TAB_WORDS
+  uint32_t *d_rowoffs = nullptr;   // 63 x 16 words: the row offsets of the two-level centre set-up (setup.cuh)
   uint32_t *d_centers = nullptr;   // 16*T
   kh::kh_u4 *d_scratch = nullptr;  // 1024*T
   uint32_t *d_flags = nullptr;     // [0] = set-up error flag (centre at infinity)

@@ -1,7 +1,7 @@
 // kh_scan.cu — context, target set, scan kernels and the scan half of the C ABI (include/keyhunt_b200.h).
 //
 // Kernels (all sm_100a, integer pipes only — there is no dense contraction on this path):
-//   kh_setup_kernel   table entries + per-thread start centres (one scalar multiplication each)
+//   kh_setup_kernel / kh_setup_fill_kernel   table entries + per-thread start centres (setup.cuh: two levels)
 //   kh_scan_kernel<K> the batch walk of walk.cuh fused with hash -> bloom -> table probe (emit.cuh)
 //   kh_bloom_build    bloom_add of every target record (atomicOr)
 //   kh_derive_kernel  private key -> public key, hash160 (both forms), ETH address
@@ -19,21 +19,37 @@ using namespace kh;
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *gtab, uint32_t *centers, uint32_t *flags) {
+// set-up, phase 1 (setup.cuh): the 513 table entries, the 63 row offsets B_j and the row bases (walkers 0, 64, 128, ...), one scalar
+// multiplication each
+__global__ void __launch_bounds__(128) kh_setup_kernel(WalkSetup ws, uint32_t *gtab, uint32_t *centers, uint32_t *rowoffs, uint32_t *flags) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_rows = (ws.T + KH_SETUP_ROW - 1) / KH_SETUP_ROW;
   if (i < KH_TAB_ENTRIES) {
     uint32_t e[16];
     setup_table_entry(e, ws, (uint32_t)i);
 #pragma unroll
     for (int k = 0; k < 16; k++) gtab[16 * i + k] = e[k];
-  } else if (i < KH_TAB_ENTRIES + ws.T) {
-    const uint64_t t = i - KH_TAB_ENTRIES;
+  } else if (i < KH_TAB_ENTRIES + (KH_SETUP_ROW - 1)) {
+    const uint32_t j = (uint32_t)(i - KH_TAB_ENTRIES) + 1;
+    uint32_t e[16];
+    setup_row_offset(e, ws, j);
+#pragma unroll
+    for (int k = 0; k < 16; k++) rowoffs[16 * (j - 1) + k] = e[k];
+  } else if (i < KH_TAB_ENTRIES + (KH_SETUP_ROW - 1) + n_rows) {
+    const uint64_t t = (i - KH_TAB_ENTRIES - (KH_SETUP_ROW - 1)) * KH_SETUP_ROW;
     fe cx, cy;
     // (an idle walker — its first batch lies beyond the segment — may sit anywhere, infinity included)
     if (!setup_center(cx, cy, ws, t) && (ws.n_batches == 0 || ws.first_batch + t < ws.n_batches)) atomicOr(flags, 1u);
 #pragma unroll
     for (int l = 0; l < 8; l++) { centers[(uint64_t)l * ws.T + t] = cx.v[l]; centers[(uint64_t)(8 + l) * ws.T + t] = cy.v[l]; }
   }
+}
+// set-up, phase 2: one thread per row of 64 walkers, 63 affine additions behind one inversion (setup_row_fill)
+__global__ void __launch_bounds__(64) kh_setup_fill_kernel(WalkSetup ws, uint32_t *centers, const uint32_t *rowoffs, uint32_t *flags) {
+  const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row * KH_SETUP_ROW >= ws.T) return;
+  fe pre[KH_SETUP_ROW - 1];
+  if (!setup_row_fill(centers, rowoffs, ws, row, pre)) atomicOr(flags, 1u);
 }
 
 // fixed-base comb of G (ec.cuh): entry (w, d) = d * 2^(8w) * G, one plain scalar multiplication each, once per context
@@ -108,6 +124,7 @@ uint64_t kh_pick_T(kh_ctx *c, uint64_t n_batches) {
 
 int kh_ensure_walk_buffers(kh_ctx *c, uint64_t T) {
   if (!c->d_gtab) KH_CUDA(c, cudaMalloc(&c->d_gtab, KH_TAB_WORDS * sizeof(uint32_t)));
+  if (!c->d_rowoffs) KH_CUDA(c, cudaMalloc(&c->d_rowoffs, (KH_SETUP_ROW - 1) * 16 * sizeof(uint32_t)));
   if (!c->d_flags) {
     KH_CUDA(c, cudaMalloc(&c->d_flags, 16 * sizeof(uint32_t)));
     KH_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(uint32_t), c->stream));
@@ -139,15 +156,17 @@ int kh_run_setup(kh_ctx *c, const WalkSetup &ws_in) {
   if (rcc) return rcc;
   WalkSetup ws = ws_in;
   ws.comb = c->d_comb;
-  const uint64_t n = KH_TAB_ENTRIES + ws.T;
+  const uint64_t n_rows = (ws.T + KH_SETUP_ROW - 1) / KH_SETUP_ROW;
+  const uint64_t n = KH_TAB_ENTRIES + (KH_SETUP_ROW - 1) + n_rows;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   kh_time_begin(c);
-  kh_setup_kernel<<<blocks, 128, 0, c->stream>>>(ws, c->d_gtab, c->d_centers, c->d_flags);
+  kh_setup_kernel<<<blocks, 128, 0, c->stream>>>(ws, c->d_gtab, c->d_centers, c->d_rowoffs, c->d_flags);
+  kh_setup_fill_kernel<<<(unsigned)((n_rows + 63) / 64), 64, 0, c->stream>>>(ws, c->d_centers, c->d_rowoffs, c->d_flags);
   KH_CUDA(c, cudaGetLastError());
   uint32_t flag = 0;
   KH_CUDA(c, cudaMemcpyAsync(&flag, c->d_flags, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
   c->stats.setup_ms += kh_time_end(c);
-  c->stats.other_launches += 1;
+  c->stats.other_launches += 2;
   KH_CUDA(c, cudaGetLastError());
   if (flag) {
     cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), c->stream);
@@ -231,7 +250,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre, c->d_comb};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre, c->d_comb, c->d_rowoffs};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);

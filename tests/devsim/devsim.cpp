@@ -7,6 +7,7 @@
 // the very code the kernels run.  This library is never loaded by keyhunt_b200 and is not a fallback:
 // the product path requires libkh_b200.so + a GPU.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -56,12 +57,64 @@ static void make_walk(const WalkSetup &ws, std::vector<uint32_t> &gtab, std::vec
   gtab.resize(KH_TAB_WORDS);
   for (uint32_t e = 0; e < KH_TAB_ENTRIES; e++) setup_table_entry(&gtab[16 * e], ws, e);
   centers.resize(16 * ws.T);
-  for (uint64_t t = 0; t < ws.T; t++) {
+  // two-level set-up exactly as kh_run_setup does it: row bases by scalar multiplication, the rest of a row by setup_row_fill
+  std::vector<uint32_t> offs(16 * (KH_SETUP_ROW - 1));
+  for (uint32_t j = 1; j < KH_SETUP_ROW; j++) setup_row_offset(&offs[16 * (j - 1)], ws, j);
+  for (uint64_t t = 0; t < ws.T; t += KH_SETUP_ROW) {
     fe cx, cy;
     setup_center(cx, cy, ws, t);
     for (int l = 0; l < 8; l++) { centers[l * ws.T + t] = cx.v[l]; centers[(8 + l) * ws.T + t] = cy.v[l]; }
   }
+  std::vector<fe> pre(KH_SETUP_ROW);
+  for (uint64_t row = 0; row * KH_SETUP_ROW < ws.T; row++) setup_row_fill(centers.data(), offs.data(), ws, row, pre.data());
+  if (getenv("KH_DEVSIM_CHECK_SETUP")) {     // the two-level centres equal the directly computed ones
+    for (uint64_t t = 0; t < ws.T; t++) {
+      fe cx, cy;
+      if (!setup_center(cx, cy, ws, t)) continue;
+      for (int l = 0; l < 8; l++)
+        if (centers[l * ws.T + t] != cx.v[l] || centers[(8 + l) * ws.T + t] != cy.v[l]) { fprintf(stderr, "devsim: two-level centre %llu differs\n", (unsigned long long)t); abort(); }
+    }
+  }
   scratch.resize((size_t)1024 * ws.T);
+}
+
+// centres of T walkers set up in two levels (setup_row_offset / setup_row_fill) against setup_center for every walker:
+// returns the number of walkers that differ (walkers at infinity are compared by their flag only); *n_inf = walkers at infinity
+int ds_setup_centres(const uint8_t k0[32], const uint8_t s[32], uint64_t T, int neg, const uint8_t *q_xy, uint64_t *n_inf) {
+  WalkSetup ws;
+  memset(&ws, 0, sizeof(ws));
+  u256_from_be(ws.k0, k0); u256_from_be(ws.s, s);
+  ws.neg = neg ? 1 : 0; ws.T = T; ws.first_batch = 0; ws.n_batches = 0; ws.comb = nullptr;
+  ws.q.inf = 1;
+  if (q_xy) { fe_from_be(ws.q.x, q_xy); fe_from_be(ws.q.y, q_xy + 32); ws.q.inf = 0; }
+  std::vector<uint32_t> gtab, centers;
+  std::vector<kh_u4> scratch;
+  std::vector<uint32_t> offs(16 * (KH_SETUP_ROW - 1));
+  centers.resize(16 * T);
+  for (uint32_t j = 1; j < KH_SETUP_ROW; j++) setup_row_offset(&offs[16 * (j - 1)], ws, j);
+  for (uint64_t t = 0; t < T; t += KH_SETUP_ROW) {
+    fe cx, cy;
+    setup_center(cx, cy, ws, t);
+    for (int l = 0; l < 8; l++) { centers[l * T + t] = cx.v[l]; centers[(8 + l) * T + t] = cy.v[l]; }
+  }
+  std::vector<fe> pre(KH_SETUP_ROW);
+  uint64_t flagged = 0;
+  for (uint64_t row = 0; row * KH_SETUP_ROW < T; row++) if (!setup_row_fill(centers.data(), offs.data(), ws, row, pre.data())) flagged++;
+  int bad = 0;
+  uint64_t inf = 0;
+  for (uint64_t t = 0; t < T; t++) {
+    fe cx, cy;
+    if (!setup_center(cx, cy, ws, t)) { inf++; continue; }
+    for (int l = 0; l < 8; l++) if (centers[l * T + t] != cx.v[l] || centers[(8 + l) * T + t] != cy.v[l]) { bad++; break; }
+  }
+  if (n_inf) *n_inf = inf;
+  if (inf && !flagged && (inf > 1 || T % KH_SETUP_ROW != 1)) {
+    // a walker at infinity that is not a row base must have been reported by its row
+    bool only_bases = true;
+    for (uint64_t t = 0; t < T; t++) { fe cx, cy; if (!setup_center(cx, cy, ws, t) && t % KH_SETUP_ROW) only_bases = false; }
+    if (!only_bases) bad += 1000000;
+  }
+  return bad;
 }
 
 // the plan of the last emulated scan (plan.hpp): out[0] = segments, out[1] = collapsed batches, out[2] = distinct T values

@@ -91,6 +91,30 @@ def test_walk_geometry(ds, oracle, start, stride, nb, T, spl):
         assert out.raw[b * 65536:(b + 1) * 65536] == oracle.batch_points(start + b * 1024 * stride, stride, True)
 
 
+def test_two_level_centre_setup(ds, oracle):
+    """setup.cuh: walker 64*i + j starts on A_i + B_j (63 affine additions behind one inversion per row) — the same points as one
+    scalar multiplication per walker, for scans, strides, giant walks (negated step, base point Q), ragged last rows, and rows
+    where a difference is zero (A_i = +-B_j: the whole row falls back) or a walker sits at infinity (reported)."""
+    ds.ds_setup_centres.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.POINTER(C.c_uint64)]
+    ninf = C.c_uint64()
+    q = oracle.pubkey(0xC0FFEE1234567)
+    qxy = be32(q[0]) + be32(q[1])
+    for k0, s, T, neg, base in [(1, 1, 130, 0, None), (0x2000000000000000, 1, 256, 0, None), (0xDEADBEEF, 977, 65, 0, None),
+                                (0x8000000000 + (1 << 31), 1 << 32, 200, 1, qxy), (5, 3, 64, 1, qxy), (7, 1, 1, 0, None), (7, 1, 63, 0, None)]:
+        assert ds.ds_setup_centres(be32(k0), be32(s), T, neg, base, C.byref(ninf)) == 0, (k0, s, T, neg)
+        assert ninf.value == 0
+    # centre of walker 64 = 5120*G = B_5: row 1 has a zero difference (doubling case) and must fall back; on the way there
+    # walker 59 crosses key n (infinity, reported by row 0)
+    assert ds.ds_setup_centres(be32(N_ORDER - 60928), be32(1), 130, 0, None, C.byref(ninf)) == 0 and ninf.value == 1
+    # the same coincidence without any walker at infinity: stride 3, walker 64 = 5120*3*G
+    assert ds.ds_setup_centres(be32(N_ORDER - 60928 * 3 + 1), be32(3), 130, 0, None, C.byref(ninf)) == 0 and ninf.value == 0
+    assert ds.ds_setup_centres(be32(N_ORDER - 60928 * 3), be32(3), 130, 0, None, C.byref(ninf)) == 0 and ninf.value == 1
+    # centre of walker 64 = -(3*1024)*G = -B_3: walker 67 is the point at infinity, everything else is right
+    assert ds.ds_setup_centres(be32(N_ORDER - 66048 - 3072), be32(1), 130, 0, None, C.byref(ninf)) == 0 and ninf.value == 1
+    # the row BASE at infinity (walker 64 = key 0): reported by phase 1, the row's other walkers are still right where defined
+    assert ds.ds_setup_centres(be32(N_ORDER - 66048), be32(1), 130, 0, None, C.byref(ninf)) == 0 and ninf.value == 1
+
+
 def _last_plan(ds):
     out = (C.c_uint64 * 3)()
     ds.ds_last_plan(out)

@@ -47,14 +47,17 @@ def test_bsgs_binned_build_equals_direct(kh, n, k):
     and the raw bytes of sampled shards."""
     seen = {}
     try:
-        for mode in (0, 2):
+        for mode, slice_kb in ((0, None), (2, None), (2, "1")):      # a 1 KB slice: the shards are applied in many passes (as at -k 4096)
             kh.set_option("bsgs_binned_build", mode)
+            if slice_kb:
+                os.environ["KH_BABY_SLICE_KB"] = slice_kb
             kh.bsgs_build(n, k)
-            seen[mode] = [kh.bsgs_digest(t) for t in range(5)] + [hashlib.sha256(kh.bsgs_export(1, s)).hexdigest() for s in (0, 17, 255)]
+            seen[(mode, slice_kb)] = [kh.bsgs_digest(t) for t in range(5)] + [hashlib.sha256(kh.bsgs_export(1, s)).hexdigest() for s in (0, 17, 255)]
     finally:
+        os.environ.pop("KH_BABY_SLICE_KB", None)
         kh.set_option("bsgs_binned_build", 1)
-    assert seen[0] == seen[2]
-    assert len(set(seen[0][:5])) == 5
+    assert seen[(0, None)] == seen[(2, None)] == seen[(2, "1")]
+    assert len(set(seen[(0, None)][:5])) == 5
 
 
 def test_bsgs_search_finds_planted_keys(kh, oracle):
