@@ -57,13 +57,15 @@ STEP_POINTS = 1 << 32
 
 # algorithmic 32-bit integer ops per point (the constants the roofline uses).
 # ops = the SURVEY constant minus 162 per hashed record: the exact prefix bitmap (emit.cuh prefilter_pass, ~8 ops) answers
-# for the 170-op bloom_check of a non-member, so that work is no longer done and must not be counted as achieved.
+# for the 170-op bloom_check of a non-member, so that work is no longer done and must not be counted as achieved.  Likewise the
+# message schedule of the second SHA-256 block of the uncompressed key (48 words x 10 ops in SURVEY's count) is looked up in a
+# 256-row table since round 2 (hash.cuh KH_SHA_UNC2_TAB) and is not counted: C2 ops = 9950 - 3*162 - 480.
 # cpu_rate = expected Mkeys/s per host thread of the reference (only used to size its bounded sample).
 WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
                start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3971),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
-               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162, disp=1,
+               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162 - 480, disp=1,
                cpu_rate=1.4, binding="alu",
                alu_ops=6993),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 41.90 G warp instructions per 2^27 points, 70.0 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",

@@ -66,6 +66,9 @@ struct ScanTargets {
   // warp.  Always present: "prefilter" = 0 uploads an all-ones bitmap.
   uint32_t pre_k;
   const uint32_t *pre;
+  // message schedules of the second SHA-256 block of the uncompressed key (hash.cuh KH_SHA_UNC2_TAB): KH_SHA2TAB_WORDS words in
+  // global memory; the scan kernels that hash uncompressed keys copy them into shared memory
+  const uint32_t *sha2;
 };
 KH_HD bool prefilter_pass(const ScanTargets &tg, uint32_t first_word_be) {
   const uint32_t idx = first_word_be >> (32 - tg.pre_k);
@@ -101,8 +104,10 @@ struct ScanEmit {
 #endif
   static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT || ENDO);
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
+  static constexpr bool SHA2TAB = KH_SHA_UNC2_TAB && (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH);   // kernels that stage the table
   const ScanTargets &tg;
-  KH_HDM explicit ScanEmit(const ScanTargets &t) : tg(t) {}
+  const uint32_t *sha2;      // the schedule table where the hash jobs read it (shared memory on the device), nullptr = compute
+  KH_HDM explicit ScanEmit(const ScanTargets &t, const uint32_t *sha2tab = nullptr) : tg(t), sha2(sha2tab) {}
 
   KH_HDM void probe(const uint32_t h[5], uint32_t kind, uint64_t batch, uint32_t idx, uint32_t variant = 0) {
     if (VANITY) {                                      // -m vanity (keyhunt.cpp:4129, :4192, :4259)
@@ -151,7 +156,7 @@ struct ScanEmit {
         for (int j = j0; j < j1; j++) {
           fe yy = y;
           if (NEED_Y && j == 3) fe_neg(yy, y);
-          hash160_job<NEED_Y>(h, j < 2 ? j : 2, xv, yy);
+          hash160_job<NEED_Y>(h, j < 2 ? j : 2, xv, yy, sha2);
           probe(h, j < 2 ? (uint32_t)j : (uint32_t)KH_KIND_UNCOMP, batch, idx, j < 2 ? (uint32_t)(2 * v + j) : (uint32_t)(6 + 2 * v + (j - 2)));
         }
       }
@@ -184,7 +189,7 @@ struct ScanEmit {
       const int j0 = (KIND == KH_SCAN_UNCOMP) ? 2 : 0, j1 = (KIND == KH_SCAN_COMP) ? 2 : 3;
 #pragma unroll 1
       for (int job = j0; job < j1; job++) {
-        hash160_job<NEED_Y>(h, job, x, y);
+        hash160_job<NEED_Y>(h, job, x, y, sha2);
         probe(h, (uint32_t)job, batch, idx);   // KH_KIND_COMP02 = 0, COMP03 = 1, UNCOMP = 2
       }
     }

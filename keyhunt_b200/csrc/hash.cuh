@@ -166,12 +166,33 @@ KH_HD uint32_t sha_k(int i) {
 #ifndef KH_SHA_SPECIAL
 #define KH_SHA_SPECIAL 1
 #endif
-KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16], int shape = 0) {
+// The second block of the 65-byte uncompressed key holds ONE byte of data (the last byte of Y, then 0x80, zeros and the length
+// 0x208): its whole 64-word message schedule is a function of that byte.  KH_SHA_UNC2_TAB = 1: the scan kernels keep the 256
+// schedules in shared memory (sha_unc2_table_fill; rows padded to 68 words so that the rows of the lanes of a quarter-warp fall on
+// different 16-byte bank groups) and `row` replaces the 48 schedule expansions of that block by 16 LDS.128 (~320 ALU-pipe
+// instructions less per uncompressed key, on kernels that are ALU-pipe bound).  row == nullptr: the schedule is computed.
+#ifndef KH_SHA_UNC2_TAB
+#define KH_SHA_UNC2_TAB 1
+#endif
+#define KH_SHA2TAB_STRIDE 68
+#define KH_SHA2TAB_WORDS (256 * KH_SHA2TAB_STRIDE)
+KH_HD void sha_load16(uint32_t w[16], const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w; w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
+#else
+  for (int i = 0; i < 16; i++) w[i] = p[i];
+#endif
+}
+KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16], int shape = 0, const uint32_t *row = nullptr) {
   uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #if KH_SHA_ROLLED
 #pragma unroll 1
   for (int kb = 0; kb < 64; kb += 16) {
-    if (KH_SHA_SPECIAL && kb == 16 && shape == 1) { KH_SHA256_EXPAND16_COMP33(w); }
+    if (KH_SHA_UNC2_TAB && row) { sha_load16(w, row + kb); }
+    else if (KH_SHA_SPECIAL && kb == 16 && shape == 1) { KH_SHA256_EXPAND16_COMP33(w); }
     else if (KH_SHA_SPECIAL && kb == 16 && shape == 2) { KH_SHA256_EXPAND16_UNC2(w); }
     else if (kb) { KH_SHA256_EXPAND16(w); }
     KH_SHA256_ROUNDS16(a, b, c, d, e, f, g, h, w, kb);
@@ -180,6 +201,19 @@ KH_HD void sha256_compress(uint32_t st[8], uint32_t w[16], int shape = 0) {
   KH_SHA256_ROUNDS(a, b, c, d, e, f, g, h, w);
 #endif
   st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+// schedule table of the second block of the uncompressed key: row v = W[0..63] for the last Y byte v
+KH_HD void sha_unc2_table_row(uint32_t *row, uint32_t v) {
+  uint32_t w[64];
+  w[0] = (v << 24) | 0x00800000u;
+  for (int i = 1; i < 15; i++) w[i] = 0;
+  w[15] = 0x208u;
+  for (int i = 16; i < 64; i++) {
+    const uint32_t x = w[i - 15], y = w[i - 2];
+    w[i] = w[i - 16] + w[i - 7] + (rotr32(x, 7) ^ rotr32(x, 18) ^ (x >> 3)) + (rotr32(y, 17) ^ rotr32(y, 19) ^ (y >> 10));
+  }
+  for (int i = 0; i < 64; i++) row[i] = w[i];
+  for (int i = 64; i < KH_SHA2TAB_STRIDE; i++) row[i] = 0;
 }
 KH_HD void sha256_init(uint32_t st[8]) {
   st[0] = 0x6a09e667u; st[1] = 0xbb67ae85u; st[2] = 0x3c6ef372u; st[3] = 0xa54ff53au;
@@ -244,7 +278,7 @@ KH_HD void hash160_uncompressed(uint32_t out[5], const fe &x, const fe &y) {
 // blocks; only when WITH_UNCOMP).  The scan kernel loops over jobs with `#pragma unroll 1`, so its hot
 // loop holds each hash body once (instruction-cache footprint, see sha256_compress).
 template <bool WITH_UNCOMP>
-KH_HD void hash160_job(uint32_t out[5], int job, const fe &x, const fe &y) {
+KH_HD void hash160_job(uint32_t out[5], int job, const fe &x, const fe &y, const uint32_t *sha2tab = nullptr) {
   uint32_t w[16], st[8];
   sha256_init(st);
   const bool unc = WITH_UNCOMP && (job == 2);
@@ -265,13 +299,13 @@ KH_HD void hash160_job(uint32_t out[5], int job, const fe &x, const fe &y) {
         w[9] = 0; w[10] = 0; w[11] = 0; w[12] = 0; w[13] = 0; w[14] = 0;
         w[15] = 0x108u;
       }
-    } else {
+    } else if (!(KH_SHA_UNC2_TAB && sha2tab)) {
       w[0] = (y.v[0] << 24) | 0x00800000u;
 #pragma unroll
       for (int i = 1; i < 15; i++) w[i] = 0;
       w[15] = 0x208u;
     }
-    sha256_compress(st, w, blk ? 2 : (unc ? 0 : 1));
+    sha256_compress(st, w, blk ? 2 : (unc ? 0 : 1), (WITH_UNCOMP && blk && sha2tab) ? sha2tab + (y.v[0] & 0xFFu) * KH_SHA2TAB_STRIDE : nullptr);
   }
   ripemd160_of_sha(out, st);
 }

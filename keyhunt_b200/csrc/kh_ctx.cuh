@@ -41,6 +41,7 @@ struct kh_ctx {
   uint32_t *d_centers = nullptr;   // 16*T
   kh::kh_u4 *d_scratch = nullptr;  // 1024*T
   uint32_t *d_flags = nullptr;     // [0] = set-up error flag (centre at infinity)
+  uint32_t *d_sha2 = nullptr;      // 256 x 68 words: SHA-256 schedules of the uncompressed key's second block (hash.cuh)
   uint32_t *d_comb = nullptr;      // fixed-base comb of G: 32 x 256 points (ec.cuh ge_mul_g_comb), built on first use
 
   // scan targets

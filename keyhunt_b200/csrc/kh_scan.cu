@@ -250,7 +250,7 @@ void kh_destroy(kh_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->d_gtab, c->d_centers, c->d_scratch, c->d_flags, c->d_bloom, c->d_table, c->d_hits, c->d_hit_count,
-                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre, c->d_comb, c->d_rowoffs};
+                  c->d_tier[0], c->d_tier[1], c->d_tier[2], c->d_bptable, c->d_aux_tab, c->d_vanity, c->d_pre, c->d_giant_cands, c->d_giant_cnt, c->d_giant_key, c->d_bsgs_pre, c->d_comb, c->d_rowoffs, c->d_sha2};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -469,9 +469,8 @@ int kh_get_table(kh_ctx *c, uint8_t *dst20, uint64_t cap_records, uint64_t *n_re
 
 template <int KIND>
 static cudaError_t launch_scan(kh_ctx *c, const WalkParams &wp, const ScanTargets &tg) {
-  if (c->endomorphism) kh_scan_kernel<KIND, true><<<(unsigned)(wp.T / ScanShape<KIND, true>::BLOCK), ScanShape<KIND, true>::BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
-  else kh_scan_kernel<KIND, false><<<(unsigned)(wp.T / ScanShape<KIND, false>::BLOCK), ScanShape<KIND, false>::BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
-  return cudaGetLastError();
+  if (c->endomorphism) return kh_launch_scan_kernel<KIND, true, false>(c, wp, tg);
+  return kh_launch_scan_kernel<KIND, false, false>(c, wp, tg);
 }
 
 extern "C" {
@@ -518,6 +517,14 @@ int kh_scan(kh_ctx *c, const uint8_t start_be[32], const uint8_t stride_be[32], 
   const bool vanity = (c->mode == KH_MODE_VANITY);
   tg.van = vanity ? c->d_vanity : nullptr; tg.van_n = vanity ? c->n_vanity : 0u;
   tg.pre = c->d_pre; tg.pre_k = c->pre_k;
+  if (!c->d_sha2) {                // SHA-256 schedules of the uncompressed key's second block (hash.cuh KH_SHA_UNC2_TAB), once per context
+    std::vector<uint32_t> tab(KH_SHA2TAB_WORDS);
+    for (uint32_t v = 0; v < 256; v++) sha_unc2_table_row(&tab[(size_t)v * KH_SHA2TAB_STRIDE], v);
+    KH_CUDA(c, cudaMalloc(&c->d_sha2, tab.size() * sizeof(uint32_t)));
+    KH_CUDA(c, cudaMemcpyAsync(c->d_sha2, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    KH_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  tg.sha2 = c->d_sha2;
   tg.bloom.bf = c->d_bloom; tg.bloom.bits = c->bloom_desc.bits; tg.bloom.magic = vanity ? 0ull : (~0ULL) / c->bloom_desc.bits;
   tg.bloom.stride = 0; tg.bloom.hashes = c->bloom_desc.hashes; tg.bloom.pad = 0;
   tg.table = c->d_table; tg.n = c->n_targets;

@@ -7,10 +7,8 @@ using namespace kh;
 
 template <int KIND>
 static cudaError_t launch_vanity(kh_ctx *c, const WalkParams &wp, const ScanTargets &tg) {
-  const unsigned blocks = (unsigned)(wp.T / KH_BLOCK);
-  if (c->endomorphism) kh_scan_kernel<KIND, true, true><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
-  else kh_scan_kernel<KIND, false, true><<<blocks, KH_BLOCK, KH_TAB_WORDS * sizeof(uint32_t), c->stream>>>(wp, tg);
-  return cudaGetLastError();
+  if (c->endomorphism) return kh_launch_scan_kernel<KIND, true, true>(c, wp, tg);
+  return kh_launch_scan_kernel<KIND, false, true>(c, wp, tg);
 }
 
 cudaError_t kh_launch_vanity(kh_ctx *c, int kind, const WalkParams &wp, const ScanTargets &tg) {

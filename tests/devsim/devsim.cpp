@@ -46,6 +46,15 @@ static void words_to_bytes(uint8_t out[20], const uint32_t w[5]) {
 void ds_hash160_comp(int prefix, const uint8_t x[32], uint8_t out[20]) { fe v; fe_from_be(v, x); uint32_t h[5]; hash160_compressed(h, (uint32_t)prefix, v); words_to_bytes(out, h); }
 void ds_hash160_uncomp(const uint8_t xy[64], uint8_t out[20]) { fe x, y; fe_from_be(x, xy); fe_from_be(y, xy + 32); uint32_t h[5]; hash160_uncompressed(h, x, y); words_to_bytes(out, h); }
 void ds_eth_addr(const uint8_t xy[64], uint8_t out[20]) { fe x, y; fe_from_be(x, xy); fe_from_be(y, xy + 32); uint32_t h[5]; eth_address(h, x, y); words_to_bytes(out, h); }
+// hash160 of the uncompressed key through the job form with the schedule table of the second block (hash.cuh KH_SHA_UNC2_TAB)
+void ds_hash160_uncomp_tab(const uint8_t xy[64], uint8_t out[20]) {
+  static std::vector<uint32_t> tab;
+  if (tab.empty()) { tab.resize(KH_SHA2TAB_WORDS); for (uint32_t v = 0; v < 256; v++) sha_unc2_table_row(&tab[(size_t)v * KH_SHA2TAB_STRIDE], v); }
+  fe x, y; fe_from_be(x, xy); fe_from_be(y, xy + 32);
+  uint32_t h[5];
+  hash160_job<true>(h, 2, x, y, tab.data());
+  words_to_bytes(out, h);
+}
 uint64_t ds_xxh64_20(const uint8_t b[20], uint64_t seed) { uint32_t w[5]; memcpy(w, b, 20); return xxh64_20(w, seed); }
 uint64_t ds_xxh64_32(const uint8_t b[32], uint64_t seed) { uint32_t w[8]; memcpy(w, b, 32); return xxh64_32(w, seed); }
 uint64_t ds_bloom_mod(uint64_t x, uint64_t bits) { return bloom_mod(x, bits, (~0ULL) / bits); }

@@ -67,10 +67,23 @@ def test_scalar_mult_and_hashes(ds, oracle):
         for pre in (2, 3):
             ds.ds_hash160_comp(pre, be32(x), out); assert out.raw == oracle.hash160_comp(pre, x)
         ds.ds_hash160_uncomp(be32(x) + be32(y), out); assert out.raw == oracle.hash160_uncomp(x, y)
+        ds.ds_hash160_uncomp_tab(be32(x) + be32(y), out); assert out.raw == oracle.hash160_uncomp(x, y)
         ds.ds_eth_addr(be32(x) + be32(y), out); assert out.raw == oracle.eth_addr(x, y)
         d, s = rnd.randbytes(32), rnd.randrange(2**64)
         assert ds.ds_xxh64_20(d[:20], s) == oracle.xxh64(d[:20], s)
         assert ds.ds_xxh64_32(d, s) == oracle.xxh64(d, s)
+
+
+def test_sha256_schedule_table_of_the_uncompressed_second_block(ds, oracle):
+    """hash.cuh KH_SHA_UNC2_TAB: the second SHA-256 block of 04||X||Y holds one data byte; its 256 precomputed message schedules
+    give the same hash160 as computing the schedule, for every value of that byte"""
+    out = C.create_string_buffer(20)
+    rnd = random.Random(10)
+    x = rnd.randrange(P_FIELD)
+    for v in range(256):
+        y = (rnd.randrange(P_FIELD) & ~0xFF) | v
+        ds.ds_hash160_uncomp_tab(be32(x) + be32(y), out)
+        assert out.raw == oracle.hash160_uncomp(x, y), v
 
 
 def test_bloom_exact_modulo(ds):
