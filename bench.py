@@ -63,20 +63,20 @@ STEP_POINTS = 1 << 32
 # cpu_rate = expected Mkeys/s per host thread of the reference (only used to size its bounded sample).
 WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
-               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3971),
+               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3964),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
                mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162 - 480, disp=1,
                cpu_rate=1.4, binding="alu",
-               alu_ops=6993),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 41.90 G warp instructions per 2^27 points, 70.0 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
+               alu_ops=6672),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 40.38 G warp instructions per 2^27 points, 69.3 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
                mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, disp=1,
-               cpu_rate=4.8, binding="fma_heavy", wide_mults=246),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
+               cpu_rate=4.8, binding="fma_heavy", wide_mults=251, dram_b_per_point=37.7),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
                   mode="address", crypto="btc", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5800 - 2 * 162, disp=2,
-                  cpu_rate=2.4, binding="alu", alu_ops=3971),
+                  cpu_rate=2.4, binding="alu", alu_ops=3964),
     "c5eth": dict(desc="C5 address ETH, 1024 targets (16 planted), from 0x10000000000",
                   mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162, disp=1,
-                  cpu_rate=2.1, binding="alu", alu_ops=5546),
+                  cpu_rate=2.1, binding="alu", alu_ops=5628),
 }
 N44 = 1 << 44          # C4: -n 2^44 -k 512 -> m = 2^31 baby steps
 
@@ -421,9 +421,11 @@ def roofline(env, wl, value_pts_s, pts_per_launch, launch_ms, clk):
     peak = peaks["lop3_imad_mix"] / 1e12
     nominal = env.info["sm_count"] * 64 * ((clk or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e12
     r = {"bound": "int", "achieved": achieved, "peak": peak, "unit": "Tiop/s", "frac": achieved / peak,
-         # DRAM bytes per launch: ncu --set full measured 39.23 GB for a 1.2416 G-point launch of this kernel
-         # (profiles/r01_v1_scan_both_ncu_full_summary.txt) = 31.6 B/point = the algorithmic scratch write+read
-         "traffic": 31.6 * pts_per_launch, "traffic_unit": "bytes of DRAM read+write per launch (ncu-measured 31.6 B/point x points per launch)",
+         # DRAM bytes per launch: ncu --set full on the final round-2 build (profiles/r02_*_ncu_sections.txt): 2.117 GB read + 2.181 GB
+         # written per 2^27-point launch of the C2 kernel = 32.0 B/point = the algorithmic scratch write + read (comp / uncomp / eth
+         # the same; xpoint with 10^6 targets 37.7 B/point: 3.6 MB bloom + 20 MB table + prefix bitmap on top)
+         "traffic": w.get("dram_b_per_point", 32.0) * pts_per_launch,
+         "traffic_unit": "bytes of DRAM read+write per launch (ncu-measured %.1f B/point x points per launch)" % w.get("dram_b_per_point", 32.0),
          "kernel": "kh_scan_kernel", "ops_per_point": w["ops"], "launch_ms": launch_ms,
          "peak_source": "measured live: kh_int_peak LOP3+IMAD dual-pipe rate; ALU pipe alone %.2f, IMAD %.2f, IMAD.WIDE %.2f Tiop/s"
                         % (peaks["lop3"] / 1e12, peaks["imad"] / 1e12, peaks["imad_wide"] / 1e12),
