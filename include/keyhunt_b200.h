@@ -167,7 +167,10 @@ int kh_hash_peak(kh_ctx *ctx, int blocks_per_sm, double out_blocks_per_s[2]);
  * big-endian values (b is ignored by unary ops; operands of the modular ops must be < P like everywhere on the path).
  * KH_FE_REDUCE_WIDE reduces the 512-bit value a*2^256 + b, any a and b. */
 enum { KH_FE_MUL = 0, KH_FE_SQR = 1, KH_FE_INV = 2, KH_FE_ADD = 3, KH_FE_SUB = 4, KH_FE_NEG = 5, KH_FE_MUL_OUTLINE = 6,
-       KH_FE_MULWIDE_LO = 7, KH_FE_MULWIDE_HI = 8, KH_FE_SQRWIDE_LO = 9, KH_FE_SQRWIDE_HI = 10, KH_FE_REDUCE_WIDE = 11 };
+       KH_FE_MULWIDE_LO = 7, KH_FE_MULWIDE_HI = 8, KH_FE_SQRWIDE_LO = 9, KH_FE_SQRWIDE_HI = 10, KH_FE_REDUCE_WIDE = 11,
+       /* the same operations with the OTHER form of the multiplier's final reduction: the kernels contain both (the C2 kernel keeps
+        * the straight-line conditional subtraction, the others test "is it >= P at all" first and branch) */
+       KH_FE_MUL_ALT = 12, KH_FE_SQR_ALT = 13, KH_FE_INV_ALT = 14, KH_FE_MUL_OUTLINE_ALT = 15, KH_FE_REDUCE_WIDE_ALT = 16 };
 int kh_selftest_fe(kh_ctx *ctx, int op, const uint8_t *a_be, const uint8_t *b_be, uint64_t n, uint8_t *out_be);
 
 #ifdef __cplusplus

@@ -103,6 +103,13 @@ struct ScanEmit {
 #define KH_OUTLINE_MUL 1
 #endif
   static constexpr bool OUTLINE_MUL = KH_OUTLINE_MUL && (KIND != KH_SCAN_XPOINT || ENDO);
+  // the rare-branch final reduction of the multiplier (fe.cuh KH_RARE_REDUCE) pays everywhere (x-only walk +4.2 %, giant +2.6 %, compress /
+  // uncompress / ETH +1 %) except in the C2 kernel, which loses 0.5 % to it (A/B profiles/r02_ab_rare_reduce.txt): that kernel keeps the
+  // straight-line form
+#ifndef KH_RARE_REDUCE_BOTH
+#define KH_RARE_REDUCE_BOTH 0
+#endif
+  static constexpr int RARE_REDUCE = (KIND == KH_SCAN_BOTH) ? (KH_RARE_REDUCE && KH_RARE_REDUCE_BOTH) : KH_RARE_REDUCE;
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
   static constexpr bool SHA2TAB = KH_SHA_UNC2_TAB && (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH);   // kernels that stage the table
   const ScanTargets &tg;
@@ -129,8 +136,8 @@ struct ScanEmit {
 #pragma unroll 1
     for (int v = 0; v < 3; v++) {
       fe xv = x;
-      if (v == 1) fe_mul_sel<OUTLINE_MUL>(xv, x, b1);
-      if (v == 2) fe_mul_sel<OUTLINE_MUL>(xv, x, b2);
+      if (v == 1) fe_mul_sel<OUTLINE_MUL, RARE_REDUCE>(xv, x, b1);
+      if (v == 2) fe_mul_sel<OUTLINE_MUL, RARE_REDUCE>(xv, x, b2);
       if (KIND == KH_SCAN_XPOINT) {
 #pragma unroll
         for (int i = 0; i < 5; i++) h[i] = bswap32(xv.v[7 - i]);
@@ -140,7 +147,7 @@ struct ScanEmit {
         // slot 2v: (xv, y) — except slot 4, where the reference hashes the BETA point again (keyhunt.cpp:3534);
         // slot 2v+1: (xv, -y)
         fe xe = xv;
-        if (v == 2) fe_mul_sel<OUTLINE_MUL>(xe, x, b1);
+        if (v == 2) fe_mul_sel<OUTLINE_MUL, RARE_REDUCE>(xe, x, b1);
         eth_address(h, xe, y);
         probe(h, KH_KIND_ETH, batch, idx, (uint32_t)(2 * v));
         fe ny;                                           // negated on the spot: one fe less alive across the candidate loop
@@ -278,6 +285,7 @@ struct BabyBins {
 struct BabyEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
+  static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
   static constexpr bool PAIRS = true;
   KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
     const fe dummy = xa;
@@ -351,6 +359,7 @@ struct GiantParams {
 struct GiantEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = KH_GIANT_OUTLINE != 0;
+  static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
   static constexpr bool PAIRS = true;
   KH_HDM void push(uint64_t batch, uint32_t idx) {
     uint32_t slot = kh_atomic_inc(gp.count);

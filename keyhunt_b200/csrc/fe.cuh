@@ -306,7 +306,11 @@ KH_HD void fe_mul_wide(uint32_t r[16], const fe &a, const fe &b) {
   kh_combine_eo(r, e, o);
 }
 
+#ifndef KH_RARE_REDUCE
+#define KH_RARE_REDUCE 1
+#endif
 // ---- 512 -> 256 (mod P), canonical ------------------------------------------------------------------
+template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
   // t = lo + hi*977 + (hi << 32), 10 limbs
   uint32_t e[9], o[9];
@@ -332,17 +336,47 @@ KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
   for (int i = 0; i < 7; i++) t[1 + i] = s[i];
   top0 = s[7];
   // second fold: top = top0 + top1*2^32 (< 2^35): t += top*977 + (top << 32)
+  if (RR) {
+  // one 8-limb addition instead of two (top*977 and top << 32 are added together first: three small limbs), and the final
+  // conditional subtraction of P as a branch that is practically never taken: the folded value t + cf*2^256 is >= P only if it
+  // overflowed 2^256 (cf) or its limbs 2..7 are all ones — probability ~2^-190 on field elements that come out of a multiplication
+  // — so the common case tests that (3 LOP3 + 1 ISETP) instead of running the 8 additions + 8 selects of fe_final_reduce.  The result
+  // is canonical either way (tests/test_gpu_field.py forces both cases on the device).
+  uint32_t g[8];
+  {
+    const uint32_t lo977 = top0 * 977u, hi977 = kh_umulhi(top0, 977u) + top1 * 977u;   // top*977 < 2^45
+    // g = top*977 + (top << 32): limb0 = lo977, limb1 = hi977 + top0, limb2 = top1 + carry, limb3 = carry
+    const uint32_t g1 = hi977 + top0;
+    const uint32_t c1 = (g1 < hi977) ? 1u : 0u;
+    const uint32_t g2 = top1 + c1;
+    g[0] = lo977; g[1] = g1; g[2] = g2; g[3] = (g2 < c1) ? 1u : 0u; g[4] = 0; g[5] = 0; g[6] = 0; g[7] = 0;
+  }
+  const uint32_t cf2 = kh_add8(t, t, g);
+  const uint32_t ones = t[2] & t[3] & t[4] & t[5] & t[6] & t[7];
+#if defined(__CUDA_ARCH__)
+  if (__builtin_expect((cf2 != 0) | (ones == 0xFFFFFFFFu), 0)) {
+#else
+  if ((cf2 != 0) | (ones == 0xFFFFFFFFu)) {
+#endif
+    fe_final_reduce(r, t, cf2);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  }
+  } else {
   const uint32_t f1[8] = {top0 * 977u, kh_umulhi(top0, 977u) + top1 * 977u, top1, 0, 0, 0, 0, 0};
   const uint32_t f2[8] = {0, top0, 0, 0, 0, 0, 0, 0};
   uint32_t cfa = kh_add8(t, t, f1);
   uint32_t cfb = kh_add8(t, t, f2);
   fe_final_reduce(r, t, cfa | cfb);
+  }
 }
 
+template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_mul(fe &r, const fe &a, const fe &b) {
   uint32_t w[16];
   fe_mul_wide(w, a, b);
-  fe_reduce_wide(r, w);
+  fe_reduce_wide<RR>(r, w);
 }
 // a^2 with 36 instead of 64 wide multiplies: off-diagonal products once (even/odd columns as in
 // fe_mul_wide), doubled, plus the eight squares.  Used where the FMA-heavy pipe is the bottleneck
@@ -375,28 +409,32 @@ KH_HD void fe_sqr_wide(uint32_t r[16], const fe &a) {
   kh_combine_eo(t, e, o);
   kh_double_add_squares(r, t, v);
 }
+template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_sqr(fe &r, const fe &a) {
   uint32_t w[16];
   fe_sqr_wide(w, a);
-  fe_reduce_wide(r, w);
+  fe_reduce_wide<RR>(r, w);
 }
 
 // Out-of-line multiply: the hash-heavy scan kernels are instruction-fetch bound (ncu: stall no_instruction,
 // GPC instruction-cache requests at >90 % of peak), so their EC loop calls ONE shared copy of the multiplier
 // instead of inlining ~2.4 KB of code at each of its eight call sites.  Operands travel by value (registers).
 #if defined(__CUDACC__)
+template <int RR = KH_RARE_REDUCE>
 static __device__ __noinline__ fe fe_mul_ol(fe a, fe b) {
   fe r;
-  fe_mul(r, a, b);
+  fe_mul<RR>(r, a, b);
   return r;
 }
 #endif
-template <bool OUTLINE>
+// RR: the form of the final reduction (KH_RARE_REDUCE); a kernel picks ONE value for every multiplication it contains, so that it
+// holds one out-of-line copy
+template <bool OUTLINE, int RR = KH_RARE_REDUCE>
 KH_HD void fe_mul_sel(fe &r, const fe &a, const fe &b) {
 #if defined(__CUDA_ARCH__)
-  if (OUTLINE) { r = fe_mul_ol(a, b); return; }
+  if (OUTLINE) { r = fe_mul_ol<RR>(a, b); return; }
 #endif
-  fe_mul(r, a, b);
+  fe_mul<RR>(r, a, b);
 }
 
 // r = a^(2^n)
@@ -410,18 +448,21 @@ KH_HD void fe_sqr_n(fe &r, const fe &a, int n) {
 // 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1).  inv(0) = 0, like Int::ModInv's "no inverse" result.
 // Cold code (once per 1024 points): on the device every multiply goes through the shared out-of-line copy
 // so that the inversion does not flush the hot loop out of the instruction cache.
+template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_mul_cold(fe &r, const fe &a, const fe &b) {
 #if defined(__CUDA_ARCH__)
-  r = fe_mul_ol(a, b);
+  r = fe_mul_ol<RR>(a, b);
 #else
-  fe_mul(r, a, b);
+  fe_mul<RR>(r, a, b);
 #endif
 }
+template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_sqr_n_cold(fe &r, const fe &a, int n) {
   r = a;
 #pragma unroll 1
-  for (int i = 0; i < n; i++) fe_mul_cold(r, r, r);
+  for (int i = 0; i < n; i++) fe_mul_cold<RR>(r, r, r);
 }
+template <int RR = KH_RARE_REDUCE>
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
@@ -429,21 +470,21 @@ static
 #endif
 void fe_inv(fe &r, const fe &a) {
   fe x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223, t;
-  fe_mul_cold(x2, a, a); fe_mul_cold(x2, x2, a);
-  fe_mul_cold(x3, x2, x2); fe_mul_cold(x3, x3, a);
-  fe_sqr_n_cold(x6, x3, 3); fe_mul_cold(x6, x6, x3);
-  fe_sqr_n_cold(x9, x6, 3); fe_mul_cold(x9, x9, x3);
-  fe_sqr_n_cold(x11, x9, 2); fe_mul_cold(x11, x11, x2);
-  fe_sqr_n_cold(x22, x11, 11); fe_mul_cold(x22, x22, x11);
-  fe_sqr_n_cold(x44, x22, 22); fe_mul_cold(x44, x44, x22);
-  fe_sqr_n_cold(x88, x44, 44); fe_mul_cold(x88, x88, x44);
-  fe_sqr_n_cold(x176, x88, 88); fe_mul_cold(x176, x176, x88);
-  fe_sqr_n_cold(x220, x176, 44); fe_mul_cold(x220, x220, x44);
-  fe_sqr_n_cold(x223, x220, 3); fe_mul_cold(x223, x223, x3);
-  fe_sqr_n_cold(t, x223, 23); fe_mul_cold(t, t, x22);
-  fe_sqr_n_cold(t, t, 5); fe_mul_cold(t, t, a);
-  fe_sqr_n_cold(t, t, 3); fe_mul_cold(t, t, x2);
-  fe_sqr_n_cold(t, t, 2); fe_mul_cold(r, t, a);
+  fe_mul_cold<RR>(x2, a, a); fe_mul_cold<RR>(x2, x2, a);
+  fe_mul_cold<RR>(x3, x2, x2); fe_mul_cold<RR>(x3, x3, a);
+  fe_sqr_n_cold<RR>(x6, x3, 3); fe_mul_cold<RR>(x6, x6, x3);
+  fe_sqr_n_cold<RR>(x9, x6, 3); fe_mul_cold<RR>(x9, x9, x3);
+  fe_sqr_n_cold<RR>(x11, x9, 2); fe_mul_cold<RR>(x11, x11, x2);
+  fe_sqr_n_cold<RR>(x22, x11, 11); fe_mul_cold<RR>(x22, x22, x11);
+  fe_sqr_n_cold<RR>(x44, x22, 22); fe_mul_cold<RR>(x44, x44, x22);
+  fe_sqr_n_cold<RR>(x88, x44, 44); fe_mul_cold<RR>(x88, x88, x44);
+  fe_sqr_n_cold<RR>(x176, x88, 88); fe_mul_cold<RR>(x176, x176, x88);
+  fe_sqr_n_cold<RR>(x220, x176, 44); fe_mul_cold<RR>(x220, x220, x44);
+  fe_sqr_n_cold<RR>(x223, x220, 3); fe_mul_cold<RR>(x223, x223, x3);
+  fe_sqr_n_cold<RR>(t, x223, 23); fe_mul_cold<RR>(t, t, x22);
+  fe_sqr_n_cold<RR>(t, t, 5); fe_mul_cold<RR>(t, t, a);
+  fe_sqr_n_cold<RR>(t, t, 3); fe_mul_cold<RR>(t, t, x2);
+  fe_sqr_n_cold<RR>(t, t, 2); fe_mul_cold<RR>(r, t, a);
 }
 
 // Inversion with operands in registers: fe_inv takes references, which makes its arguments address-taken locals of the

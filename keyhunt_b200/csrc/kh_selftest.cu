@@ -41,6 +41,16 @@ __global__ void __launch_bounds__(128) kh_selftest_fe_kernel(int op, const uint3
       for (int l = 0; l < 8; l++) { w[l] = b.v[l]; w[8 + l] = a.v[l]; }
       fe_reduce_wide(r, w);
       break;
+    // the other form of the multiplier's final reduction (fe.cuh KH_RARE_REDUCE): the kernels use both (emit.cuh RARE_REDUCE)
+    case KH_FE_MUL_ALT: fe_mul<!KH_RARE_REDUCE>(r, a, b); break;
+    case KH_FE_SQR_ALT: fe_sqr<!KH_RARE_REDUCE>(r, a); break;
+    case KH_FE_INV_ALT: fe_inv<!KH_RARE_REDUCE>(r, a); break;
+    case KH_FE_MUL_OUTLINE_ALT: r = fe_mul_ol<!KH_RARE_REDUCE>(a, b); break;
+    case KH_FE_REDUCE_WIDE_ALT:
+#pragma unroll
+      for (int l = 0; l < 8; l++) { w[l] = b.v[l]; w[8 + l] = a.v[l]; }
+      fe_reduce_wide<!KH_RARE_REDUCE>(r, w);
+      break;
     default: break;
   }
 #pragma unroll
@@ -49,7 +59,7 @@ __global__ void __launch_bounds__(128) kh_selftest_fe_kernel(int op, const uint3
 
 extern "C" int kh_selftest_fe(kh_ctx *c, int op, const uint8_t *a_be, const uint8_t *b_be, uint64_t n, uint8_t *out_be) {
   if (!c || !a_be || !b_be || !out_be) return KH_EINVAL;
-  if (op < KH_FE_MUL || op > KH_FE_REDUCE_WIDE) return kh_fail(c, KH_EINVAL, "unknown field op %d", op);
+  if (op < KH_FE_MUL || op > KH_FE_REDUCE_WIDE_ALT) return kh_fail(c, KH_EINVAL, "unknown field op %d", op);
   if (n == 0) return KH_OK;
   cudaSetDevice(c->device);
   std::vector<uint32_t> ha(8 * n), hb(8 * n), ho(8 * n);

@@ -91,6 +91,7 @@ KH_HD void scratch_load(fe &a, const kh_u4 *s, uint64_t T, uint64_t t, int e) {
 template <class Emit>
 KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, Emit &emit) {
   constexpr bool OL = Emit::OUTLINE_MUL;   // one shared multiplier copy in instruction-fetch-bound kernels
+  constexpr int RR = Emit::RARE_REDUCE;    // form of the multiplier's final reduction (fe.cuh KH_RARE_REDUCE), one per kernel
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; l++) { px.v[l] = wp.centers[(uint64_t)l * wp.T + t]; py.v[l] = wp.centers[(uint64_t)(8 + l) * wp.T + t]; }
@@ -107,11 +108,11 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       fe gx, dx;
       tab_load_x(gx, tab, e);
       fe_sub(dx, gx, px);
-      if (e == 0) acc = dx; else fe_mul_sel<OL>(acc, acc, dx);
+      if (e == 0) acc = dx; else fe_mul_sel<OL, RR>(acc, acc, dx);
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
     fe inv;
-    fe_inv(inv, acc);   // one inversion per 1024 points (+ the centre move)
+    fe_inv<RR>(inv, acc);   // one inversion per 1024 points (+ the centre move)
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1
@@ -121,9 +122,9 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e > 0) {
         fe pre, dx;
         scratch_load(pre, wp.scratch, wp.T, t, e - 1);
-        fe_mul_sel<OL>(dinv, pre, inv);       // 1/dx_e
+        fe_mul_sel<OL, RR>(dinv, pre, inv);       // 1/dx_e
         fe_sub(dx, gx, px);
-        fe_mul_sel<OL>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
+        fe_mul_sel<OL, RR>(inv, inv, dx);         // 1/(dx_0 ... dx_{e-1})
       } else {
         dinv = inv;
       }
@@ -133,9 +134,9 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
         fe dyp, dym, sp, sm, xp, xm, c;
         fe_sub(dyp, gy, py);
         fe_add(dym, gy, py);
-        fe_mul_sel<OL>(sp, dyp, dinv);
-        fe_mul_sel<OL>(sm, dym, dinv);
-        if (OL) { fe_mul_sel<true>(xp, sp, sp); fe_mul_sel<true>(xm, sm, sm); } else { fe_sqr(xp, sp); fe_sqr(xm, sm); }
+        fe_mul_sel<OL, RR>(sp, dyp, dinv);
+        fe_mul_sel<OL, RR>(sm, dym, dinv);
+        if (OL) { fe_mul_sel<true, RR>(xp, sp, sp); fe_mul_sel<true, RR>(xm, sm, sm); } else { fe_sqr<RR>(xp, sp); fe_sqr<RR>(xm, sm); }
         fe_add(c, px, gx);
         fe_sub(xp, xp, c);
         fe_sub(xm, xm, c);
@@ -154,19 +155,19 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
           fe s, dy, s2;
           if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
-          fe_mul_sel<OL>(s, dy, dinv);
-          if (OL) fe_mul_sel<true>(s2, s, s); else fe_sqr(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
+          fe_mul_sel<OL, RR>(s, dy, dinv);
+          if (OL) fe_mul_sel<true, RR>(s2, s, s); else fe_sqr<RR>(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
           fe_sub(x3, s2, px);
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
-            fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy);
+            fe_sub(y3, gx, x3); fe_mul_sel<OL, RR>(y3, y3, s); fe_sub(y3, y3, gy);
             px = x3; py = y3;
             do_emit = false;
             idx = 0;
           } else {
             if (Emit::NEED_Y) {
-              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
-              else          { fe_sub(y3, x3, gx); fe_mul_sel<OL>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
+              if (sgn == 0) { fe_sub(y3, gx, x3); fe_mul_sel<OL, RR>(y3, y3, s); fe_sub(y3, y3, gy); }   // s*(gx-x3) - gy
+              else          { fe_sub(y3, x3, gx); fe_mul_sel<OL, RR>(y3, y3, s); fe_add(y3, y3, gy); }   // s'*(x3-gx) + gy, s' = -s
             } else {
               y3 = py;
             }

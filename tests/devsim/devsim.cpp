@@ -34,6 +34,16 @@ void ds_fe_reduce_wide(const uint8_t hi[32], const uint8_t lo[32], uint8_t out[3
   fe_reduce_wide(r, w); fe_to_be(out, r);
 }
 void ds_fe_inv(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_inv(r, x); fe_to_be(out, r); }
+// the other form of the multiplier's final reduction (fe.cuh KH_RARE_REDUCE; the kernels contain both)
+void ds_fe_mul_alt(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { fe x, y, r; fe_from_be(x, a); fe_from_be(y, b); fe_mul<!KH_RARE_REDUCE>(r, x, y); fe_to_be(out, r); }
+void ds_fe_sqr_alt(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_sqr<!KH_RARE_REDUCE>(r, x); fe_to_be(out, r); }
+void ds_fe_inv_alt(const uint8_t a[32], uint8_t out[32]) { fe x, r; fe_from_be(x, a); fe_inv<!KH_RARE_REDUCE>(r, x); fe_to_be(out, r); }
+void ds_fe_reduce_wide_alt(const uint8_t hi[32], const uint8_t lo[32], uint8_t out[32]) {
+  fe h, l, r; fe_from_be(h, hi); fe_from_be(l, lo);
+  uint32_t w[16];
+  for (int i = 0; i < 8; i++) { w[i] = l.v[i]; w[8 + i] = h.v[i]; }
+  fe_reduce_wide<!KH_RARE_REDUCE>(r, w); fe_to_be(out, r);
+}
 
 void ds_pubkey(const uint8_t key[32], uint8_t xy[64]) {
   u256 k; u256_from_be(k, key);
@@ -237,6 +247,7 @@ int64_t ds_scan(int kind, const uint8_t *table20, uint64_t n_targets, const uint
 struct DumpEmit {
   static constexpr bool NEED_Y = true;
   static constexpr bool OUTLINE_MUL = false;
+  static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
   static constexpr bool PAIRS = false;
   void pair(const fe &, uint32_t, const fe &, uint32_t, uint64_t) {}
   uint8_t *out;

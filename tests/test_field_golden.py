@@ -59,14 +59,18 @@ def test_devsim_field_ops():
     ds = C.CDLL(os.path.join(d, "libkh_devsim.so"))
     fns = {"mul": (ds.ds_fe_mul, 2), "sqr": (ds.ds_fe_sqr, 1), "inv": (ds.ds_fe_inv, 1), "add": (ds.ds_fe_add, 2), "sub": (ds.ds_fe_sub, 2),
            "neg": (ds.ds_fe_neg, 1), "reduce": (ds.ds_fe_reduce_wide, 2)}
+    alt = {"mul": (ds.ds_fe_mul_alt, 2), "sqr": (ds.ds_fe_sqr_alt, 1), "inv": (ds.ds_fe_inv_alt, 1), "reduce": (ds.ds_fe_reduce_wide_alt, 2)}
     for v in VEC:
-        fn, n = fns[v["op"]]
-        o = C.create_string_buffer(32)
-        if n == 2:
-            fn(be32(I(v["a"])), be32(I(v["b"])), o)
-        else:
-            fn(be32(I(v["a"])), o)
-        assert int.from_bytes(o.raw, "big") == I(v["r"]), v
+        for table in (fns, alt):          # both forms of the multiplier's final reduction (fe.cuh KH_RARE_REDUCE)
+            if v["op"] not in table:
+                continue
+            fn, n = table[v["op"]]
+            o = C.create_string_buffer(32)
+            if n == 2:
+                fn(be32(I(v["a"])), be32(I(v["b"])), o)
+            else:
+                fn(be32(I(v["a"])), o)
+            assert int.from_bytes(o.raw, "big") == I(v["r"]), v
 
 
 @pytest.mark.ref

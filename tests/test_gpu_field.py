@@ -16,6 +16,8 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 PRIM = json.load(open(os.path.join(GOLD, "primitives.json")))
 EDGE = json.load(open(os.path.join(GOLD, "field_edge.json")))["vectors"]
 OPS = {"mul": K.FE_MUL, "sqr": K.FE_SQR, "inv": K.FE_INV, "add": K.FE_ADD, "sub": K.FE_SUB, "neg": K.FE_NEG, "reduce": K.FE_REDUCE_WIDE}
+# the kernels contain two forms of the multiplier's final reduction (fe.cuh KH_RARE_REDUCE / emit.cuh RARE_REDUCE): both are tested
+ALT = {"mul": K.FE_MUL_ALT, "sqr": K.FE_SQR_ALT, "inv": K.FE_INV_ALT, "reduce": K.FE_REDUCE_WIDE_ALT}
 
 
 def I(s):
@@ -26,11 +28,15 @@ def test_reference_vectors_on_device(kh):
     a, b, r = zip(*[(I(x), I(y), I(z)) for x, y, z in PRIM["fe_mul"]])
     assert kh.selftest_fe(K.FE_MUL, a, b) == list(r)
     assert kh.selftest_fe(K.FE_MUL_OUTLINE, a, b) == list(r)
+    assert kh.selftest_fe(K.FE_MUL_ALT, a, b) == list(r)
+    assert kh.selftest_fe(K.FE_MUL_OUTLINE_ALT, a, b) == list(r)
     a, r = zip(*[(I(x), I(z)) for x, z in PRIM["fe_sqr"]])
     assert kh.selftest_fe(K.FE_SQR, a) == list(r)
+    assert kh.selftest_fe(K.FE_SQR_ALT, a) == list(r)
     assert kh.selftest_fe(K.FE_MUL, a, a) == list(r)
     a, r = zip(*[(I(x), I(z)) for x, z in PRIM["fe_inv"]])
     assert kh.selftest_fe(K.FE_INV, a) == list(r)
+    assert kh.selftest_fe(K.FE_INV_ALT, a) == list(r)
 
 
 @pytest.mark.parametrize("op", sorted(OPS))
@@ -40,8 +46,11 @@ def test_forced_edge_operands_on_device(kh, op):
     got = kh.selftest_fe(OPS[op], [I(v["a"]) for v in vec], [I(v["b"]) for v in vec])
     bad = [(v, hex(g)) for v, g in zip(vec, got) if g != I(v["r"])]
     assert not bad, bad[:3]
+    if op in ALT:
+        assert kh.selftest_fe(ALT[op], [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
     if op == "mul":   # the shared out-of-line copy the hash kernels call, and mul(a, a) against the dedicated squaring
         assert kh.selftest_fe(K.FE_MUL_OUTLINE, [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
+        assert kh.selftest_fe(K.FE_MUL_OUTLINE_ALT, [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
     if op == "sqr":
         assert kh.selftest_fe(K.FE_MUL, [I(v["a"]) for v in vec], [I(v["a"]) for v in vec]) == got
 
@@ -68,6 +77,8 @@ def test_random_operands_match_the_oracle(kh, oracle):
     b = [rnd.randrange(P_FIELD) for _ in range(3000)]
     assert kh.selftest_fe(K.FE_MUL, a, b) == [oracle.fe_mul(x, y) for x, y in zip(a, b)]
     assert kh.selftest_fe(K.FE_SQR, a) == [oracle.fe_sqr(x) for x in a]
+    assert kh.selftest_fe(K.FE_MUL_ALT, a, b) == [oracle.fe_mul(x, y) for x, y in zip(a, b)]
+    assert kh.selftest_fe(K.FE_SQR_ALT, a) == [oracle.fe_sqr(x) for x in a]
     assert kh.selftest_fe(K.FE_ADD, a, b) == [oracle.fe_add(x, y) for x, y in zip(a, b)]
     assert kh.selftest_fe(K.FE_SUB, a, b) == [oracle.fe_sub(x, y) for x, y in zip(a, b)]
     assert kh.selftest_fe(K.FE_NEG, a) == [oracle.fe_neg(x) for x in a]
