@@ -309,16 +309,23 @@ KH_HD void fe_mul_wide(uint32_t r[16], const fe &a, const fe &b) {
 #ifndef KH_RARE_REDUCE
 #define KH_RARE_REDUCE 1
 #endif
+#ifndef KH_FOLD_IN_O
+#define KH_FOLD_IN_O 1
+#endif
 // ---- 512 -> 256 (mod P), canonical ------------------------------------------------------------------
 template <int RR = KH_RARE_REDUCE>
 KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
   // t = lo + hi*977 + (hi << 32), 10 limbs
   uint32_t e[9], o[9];
+  // KH_FOLD_IN_O: the "hi << 32" term (hi limb i at limb i+1 = o[i]) is what the o accumulator starts from, so that it rides in the
+  // carry chain of the odd products instead of costing an 8-limb addition of its own (the four odd products are then links of a
+  // chain, not plain ones)
+  constexpr bool FOLD_IN_O = KH_FOLD_IN_O != 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) { e[i] = w[i]; o[i] = 0; }
+  for (int i = 0; i < 8; i++) { e[i] = w[i]; o[i] = FOLD_IN_O ? w[8 + i] : 0u; }
   e[8] = 0; o[8] = 0;
   kh_mad_row(e, w[8], w[10], w[12], w[14], 977u);  // hi limbs 0,2,4,6 -> columns 0,2,4,6
-  if (KH_PLAIN_HEAD) {                             // o is zero: four carry-free products
+  if (KH_PLAIN_HEAD && !FOLD_IN_O) {               // o is zero: four carry-free products
     const uint32_t xo[4] = {w[9], w[11], w[13], w[15]}, y[4] = {977u, 977u, 977u, 977u};
     kh_mul_lanes<4>(o, xo, y);
   } else
@@ -328,9 +335,10 @@ KH_HD void fe_reduce_wide(fe &r, const uint32_t w[16]) {
   uint32_t s[8];
   uint32_t cf = kh_add8(s, e + 1, o);
   top1 = o[8] + cf;
-  // += hi << 32 (limbs 1..8)
-  cf = kh_add8(s, s, w + 8);
-  top1 += cf;
+  if (!FOLD_IN_O) {                                // += hi << 32 (limbs 1..8)
+    cf = kh_add8(s, s, w + 8);
+    top1 += cf;
+  }
   t[0] = e[0];
 #pragma unroll
   for (int i = 0; i < 7; i++) t[1 + i] = s[i];
