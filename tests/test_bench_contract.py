@@ -89,6 +89,19 @@ def test_r02_strong_scaling_on_two_gpus():
     assert d2["strong"]["c4"]["planted"]["planted_found"] is True
 
 
+def test_r02_eight_gpus():
+    """one 8 x B200 node (gpurun --gpus 8, tools/gpu_job_n8.sh): weak-scaled headline and the strong-scaling blocks"""
+    d1, d8 = _line(R02), _line(os.path.join(ROOT, "profiles", "r02_bench_n8.json"))
+    assert d8["n_gpus"] == 8 and d8["hits"]["all_planted_found_and_nothing_else"] is True
+    assert 7.8 < d8["value"] / d1["value"] < 8.2
+    for cur in ("c5btc", "c5eth"):
+        a, b = d1["strong"]["c5"][cur], d8["strong"]["c5"][cur]
+        assert b["planted_found_and_nothing_else"] is True and a["keys"] == b["keys"] and b["time_s"] < a["time_s"] / 7.5 and b["efficiency"] > 0.95
+    s1, s8 = d1["strong"]["c4"]["sweep"], d8["strong"]["c4"]["sweep"]
+    assert s1["giant_steps"] == s8["giant_steps"] and s8["time_s"] < s1["time_s"] / 7 and s8["efficiency"] > 0.9
+    assert d8["strong"]["c4"]["planted"]["planted_found"] is True
+
+
 def test_r02_reference_arm_agrees_with_the_inline_cpu_baseline():
     r, d = _line(R02_REF), _line(R02)
     assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
