@@ -75,6 +75,12 @@ __global__ void kh_pre_build(uint32_t *pre, uint32_t k, const uint32_t *table_be
   atomicOr(pre + (idx >> 5), 1u << (idx & 31));
 }
 
+// the uploaded 20-byte records -> 5 big-endian-packed words each (numeric order = memcmp order), in place
+__global__ void kh_table_pack(uint32_t *table, uint64_t n_words) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) table[i] = bswap32(table[i]);
+}
+
 __global__ void kh_bloom_build(BloomDev bl, const uint32_t *table_be, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -327,20 +333,18 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
   else if (kh_bloom_params(n <= 10000 ? 10000 : n, &d) != KH_OK) return kh_fail(c, KH_EINVAL, "bloom sizing failed");
   if (d.bits == 0 || d.hashes == 0 || d.bytes < (d.bits + 7) / 8) return kh_fail(c, KH_EINVAL, "bad bloom descriptor");
 
-  // sorted table (_sort keyhunt.cpp:4307: ascending memcmp order)
-  std::vector<uint64_t> order(n);
-  std::iota(order.begin(), order.end(), 0);
-  bool sorted = true;   // the reference hands over an already sorted addressTable: skip the sort then
+  // sorted table (_sort keyhunt.cpp:4307: ascending memcmp order).  The reference hands over an already sorted addressTable: then
+  // the caller's buffer goes to the device as it is (the words are packed there, kh_table_pack) and the host only keeps a copy
+  bool sorted = true;
   for (uint64_t i = 1; i < n && sorted; i++) sorted = memcmp(records20 + 20 * (i - 1), records20 + 20 * i, 20) <= 0;
-  if (!sorted)
-    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return memcmp(records20 + 20 * a, records20 + 20 * b, 20) < 0; });
   c->h_table20.resize(20 * n);
-  std::vector<uint32_t> packed(5 * n);
-  for (uint64_t i = 0; i < n; i++) {
-    const uint8_t *p = records20 + 20 * order[i];
-    memcpy(&c->h_table20[20 * i], p, 20);
-    for (int k = 0; k < 5; k++)
-      packed[5 * i + k] = ((uint32_t)p[4 * k] << 24) | ((uint32_t)p[4 * k + 1] << 16) | ((uint32_t)p[4 * k + 2] << 8) | p[4 * k + 3];
+  if (sorted) {
+    if (n) memcpy(c->h_table20.data(), records20, 20 * n);
+  } else {
+    std::vector<uint64_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return memcmp(records20 + 20 * a, records20 + 20 * b, 20) < 0; });
+    for (uint64_t i = 0; i < n; i++) memcpy(&c->h_table20[20 * i], records20 + 20 * order[i], 20);
   }
   // device buffers are kept across calls when the sizes repeat (a caller that re-sends the same target set every step)
   c->have_targets = false;
@@ -350,7 +354,11 @@ int kh_set_targets(kh_ctx *c, int mode, int crypto, int search, const uint8_t *r
     KH_CUDA(c, cudaMalloc(&c->d_table, table_bytes));
     c->table_alloc = table_bytes;
   }
-  if (n) KH_CUDA(c, cudaMemcpyAsync(c->d_table, packed.data(), 5 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (n) {
+    KH_CUDA(c, cudaMemcpyAsync(c->d_table, sorted ? records20 : c->h_table20.data(), 20 * n, cudaMemcpyHostToDevice, c->stream));
+    kh_table_pack<<<(unsigned)((5 * n + 255) / 256), 256, 0, c->stream>>>(c->d_table, 5 * n);
+    c->stats.other_launches += 1;
+  }
   const size_t bloom_alloc = (size_t)((d.bytes + 15) / 16) * 16;
   if (!c->d_bloom || c->bloom_alloc != bloom_alloc) {
     if (c->d_bloom) { cudaFree(c->d_bloom); c->d_bloom = nullptr; }
