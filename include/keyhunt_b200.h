@@ -170,7 +170,8 @@ enum { KH_FE_MUL = 0, KH_FE_SQR = 1, KH_FE_INV = 2, KH_FE_ADD = 3, KH_FE_SUB = 4
        KH_FE_MULWIDE_LO = 7, KH_FE_MULWIDE_HI = 8, KH_FE_SQRWIDE_LO = 9, KH_FE_SQRWIDE_HI = 10, KH_FE_REDUCE_WIDE = 11,
        /* the same operations with the OTHER form of the multiplier's final reduction: the kernels contain both (the C2 kernel keeps
         * the straight-line conditional subtraction, the others test "is it >= P at all" first and branch) */
-       KH_FE_MUL_ALT = 12, KH_FE_SQR_ALT = 13, KH_FE_INV_ALT = 14, KH_FE_MUL_OUTLINE_ALT = 15, KH_FE_REDUCE_WIDE_ALT = 16 };
+       KH_FE_MUL_ALT = 12, KH_FE_SQR_ALT = 13, KH_FE_INV_ALT = 14, KH_FE_MUL_OUTLINE_ALT = 15, KH_FE_REDUCE_WIDE_ALT = 16,
+       KH_FE_INV_SQR = 17 /* the inversion as the x-only walks run it: its 255 squarings through the dedicated squaring */ };
 int kh_selftest_fe(kh_ctx *ctx, int op, const uint8_t *a_be, const uint8_t *b_be, uint64_t n, uint8_t *out_be);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ EXPORTS = ["kh_create", "kh_destroy", "kh_last_error", "kh_set_option", "kh_bloo
 # kh_selftest_fe ops (include/keyhunt_b200.h)
 FE_MUL, FE_SQR, FE_INV, FE_ADD, FE_SUB, FE_NEG, FE_MUL_OUTLINE = 0, 1, 2, 3, 4, 5, 6
 FE_MULWIDE_LO, FE_MULWIDE_HI, FE_SQRWIDE_LO, FE_SQRWIDE_HI, FE_REDUCE_WIDE = 7, 8, 9, 10, 11
-FE_MUL_ALT, FE_SQR_ALT, FE_INV_ALT, FE_MUL_OUTLINE_ALT, FE_REDUCE_WIDE_ALT = 12, 13, 14, 15, 16     # the other final-reduction form
+FE_MUL_ALT, FE_SQR_ALT, FE_INV_ALT, FE_MUL_OUTLINE_ALT, FE_REDUCE_WIDE_ALT, FE_INV_SQR = 12, 13, 14, 15, 16, 17     # the other final-reduction form
 
 
 class KhError(RuntimeError):

@@ -110,6 +110,14 @@ struct ScanEmit {
 #define KH_RARE_REDUCE_BOTH 0
 #endif
   static constexpr int RARE_REDUCE = (KIND == KH_SCAN_BOTH) ? (KH_RARE_REDUCE && KH_RARE_REDUCE_BOTH) : KH_RARE_REDUCE;
+  // the inversion's 255 squarings as dedicated squarings (fe.cuh fe_sqr_n_cold): where the multiplier binds, not the instruction cache
+#ifndef KH_INV_SQR
+#define KH_INV_SQR 1
+#endif
+#ifndef KH_INV_SQR_HASH
+#define KH_INV_SQR_HASH 0
+#endif
+  static constexpr bool INV_SQR = OUTLINE_MUL ? (KH_INV_SQR_HASH != 0) : (KH_INV_SQR != 0);
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
   static constexpr bool SHA2TAB = KH_SHA_UNC2_TAB && (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH);   // kernels that stage the table
   const ScanTargets &tg;
@@ -286,6 +294,7 @@ struct BabyEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = false;
   static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
+  static constexpr bool INV_SQR = KH_INV_SQR != 0;
   static constexpr bool PAIRS = true;
   KH_HDM void pair(const fe &xa, uint32_t ia, const fe &xb, uint32_t ib, uint64_t batch) {
     const fe dummy = xa;
@@ -360,6 +369,7 @@ struct GiantEmit {
   static constexpr bool NEED_Y = false;
   static constexpr bool OUTLINE_MUL = KH_GIANT_OUTLINE != 0;
   static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
+  static constexpr bool INV_SQR = KH_INV_SQR != 0;
   static constexpr bool PAIRS = true;
   KH_HDM void push(uint64_t batch, uint32_t idx) {
     uint32_t slot = kh_atomic_inc(gp.count);

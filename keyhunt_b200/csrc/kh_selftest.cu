@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(128) kh_selftest_fe_kernel(int op, const uint3
     case KH_FE_MUL_ALT: fe_mul<!KH_RARE_REDUCE>(r, a, b); break;
     case KH_FE_SQR_ALT: fe_sqr<!KH_RARE_REDUCE>(r, a); break;
     case KH_FE_INV_ALT: fe_inv<!KH_RARE_REDUCE>(r, a); break;
+    case KH_FE_INV_SQR: fe_inv<KH_RARE_REDUCE, true>(r, a); break;      // the x-only walks' inversion: dedicated out-of-line squaring
     case KH_FE_MUL_OUTLINE_ALT: r = fe_mul_ol<!KH_RARE_REDUCE>(a, b); break;
     case KH_FE_REDUCE_WIDE_ALT:
 #pragma unroll
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(128) kh_selftest_fe_kernel(int op, const uint3
 
 extern "C" int kh_selftest_fe(kh_ctx *c, int op, const uint8_t *a_be, const uint8_t *b_be, uint64_t n, uint8_t *out_be) {
   if (!c || !a_be || !b_be || !out_be) return KH_EINVAL;
-  if (op < KH_FE_MUL || op > KH_FE_REDUCE_WIDE_ALT) return kh_fail(c, KH_EINVAL, "unknown field op %d", op);
+  if (op < KH_FE_MUL || op > KH_FE_INV_SQR) return kh_fail(c, KH_EINVAL, "unknown field op %d", op);
   if (n == 0) return KH_OK;
   cudaSetDevice(c->device);
   std::vector<uint32_t> ha(8 * n), hb(8 * n), ho(8 * n);

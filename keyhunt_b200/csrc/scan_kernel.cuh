@@ -59,14 +59,9 @@ __global__ void __launch_bounds__((ScanShape<KIND, ENDO>::BLOCK), (ScanShape<KIN
 template <int KIND, bool ENDO, bool VANITY>
 static cudaError_t kh_launch_scan_kernel(kh_ctx *c, const kh::WalkParams &wp, const kh::ScanTargets &tg) {
   constexpr size_t smem = kh_scan_smem_bytes<KIND, ENDO, VANITY>();
-  if (smem > 48 * 1024) {
-    static bool opted[16] = {};                      // per device
-    const int dev = c->device & 15;
-    if (!opted[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(kh_scan_kernel<KIND, ENDO, VANITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      opted[dev] = true;
-    }
+  if (smem > 48 * 1024) {                            // (per device and per instantiation; a few microseconds in front of a launch)
+    cudaError_t e = cudaFuncSetAttribute(kh_scan_kernel<KIND, ENDO, VANITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
   constexpr int BLOCK = ScanShape<KIND, ENDO>::BLOCK;
   kh_scan_kernel<KIND, ENDO, VANITY><<<(unsigned)(wp.T / BLOCK), BLOCK, smem, c->stream>>>(wp, tg);

@@ -112,7 +112,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
       if (e < KH_TAB_ENTRIES - 1) scratch_store(wp.scratch, wp.T, t, e, acc);
     }
     fe inv;
-    fe_inv<RR>(inv, acc);   // one inversion per 1024 points (+ the centre move)
+    fe_inv<RR, Emit::INV_SQR>(inv, acc);   // one inversion per 1024 points (+ the centre move)
 
     // ---- backward pass: peel the inverses off and produce the points ------------------------------
 #pragma unroll 1

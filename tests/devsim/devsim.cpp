@@ -248,6 +248,7 @@ struct DumpEmit {
   static constexpr bool NEED_Y = true;
   static constexpr bool OUTLINE_MUL = false;
   static constexpr int RARE_REDUCE = KH_RARE_REDUCE;
+  static constexpr bool INV_SQR = true;
   static constexpr bool PAIRS = false;
   void pair(const fe &, uint32_t, const fe &, uint32_t, uint64_t) {}
   uint8_t *out;

@@ -37,6 +37,7 @@ def test_reference_vectors_on_device(kh):
     a, r = zip(*[(I(x), I(z)) for x, z in PRIM["fe_inv"]])
     assert kh.selftest_fe(K.FE_INV, a) == list(r)
     assert kh.selftest_fe(K.FE_INV_ALT, a) == list(r)
+    assert kh.selftest_fe(K.FE_INV_SQR, a) == list(r)
 
 
 @pytest.mark.parametrize("op", sorted(OPS))
@@ -48,6 +49,8 @@ def test_forced_edge_operands_on_device(kh, op):
     assert not bad, bad[:3]
     if op in ALT:
         assert kh.selftest_fe(ALT[op], [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
+    if op == "inv":
+        assert kh.selftest_fe(K.FE_INV_SQR, [I(v["a"]) for v in vec]) == got
     if op == "mul":   # the shared out-of-line copy the hash kernels call, and mul(a, a) against the dedicated squaring
         assert kh.selftest_fe(K.FE_MUL_OUTLINE, [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
         assert kh.selftest_fe(K.FE_MUL_OUTLINE_ALT, [I(v["a"]) for v in vec], [I(v["b"]) for v in vec]) == got
@@ -83,6 +86,7 @@ def test_random_operands_match_the_oracle(kh, oracle):
     assert kh.selftest_fe(K.FE_SUB, a, b) == [oracle.fe_sub(x, y) for x, y in zip(a, b)]
     assert kh.selftest_fe(K.FE_NEG, a) == [oracle.fe_neg(x) for x in a]
     assert kh.selftest_fe(K.FE_INV, a[:300]) == [oracle.fe_inv(x) for x in a[:300]]
+    assert kh.selftest_fe(K.FE_INV_SQR, a[:300]) == [oracle.fe_inv(x) for x in a[:300]]
     # operands with long runs of ones / zeros in the limbs (carry propagation across all eight limbs)
     s = [((1 << rnd.randrange(1, 256)) - 1) ^ (((1 << rnd.randrange(1, 256)) - 1) << rnd.randrange(0, 200)) for _ in range(500)]
     s = [x % P_FIELD for x in s]
