@@ -110,14 +110,19 @@ struct ScanEmit {
 #define KH_RARE_REDUCE_BOTH 0
 #endif
   static constexpr int RARE_REDUCE = (KIND == KH_SCAN_BOTH) ? (KH_RARE_REDUCE && KH_RARE_REDUCE_BOTH) : KH_RARE_REDUCE;
-  // the inversion's 255 squarings as dedicated squarings (fe.cuh fe_sqr_n_cold): where the multiplier binds, not the instruction cache
+  // squarings (the 255 of the inversion, one per point in the walk) through a dedicated squaring (fe.cuh fe_sqr_ol / fe_sqr_sel) instead of
+  // the shared multiplier: x-only walk +1.2 %, giant +0.9 %, compress +0.9 %, uncompress +1.3 %, ETH +0.8 %; the C2 kernel loses 0.3 % to the
+  // second out-of-line copy and keeps the single multiplier (A/B profiles/r02_ab_inv_sqr.txt, r02_ab_hash_sqr_keccak_peel.txt)
 #ifndef KH_INV_SQR
 #define KH_INV_SQR 1
 #endif
 #ifndef KH_INV_SQR_HASH
-#define KH_INV_SQR_HASH 0
+#define KH_INV_SQR_HASH 1
 #endif
-  static constexpr bool INV_SQR = OUTLINE_MUL ? (KH_INV_SQR_HASH != 0) : (KH_INV_SQR != 0);
+#ifndef KH_INV_SQR_BOTH
+#define KH_INV_SQR_BOTH 0
+#endif
+  static constexpr bool INV_SQR = !OUTLINE_MUL ? (KH_INV_SQR != 0) : ((KIND == KH_SCAN_BOTH) ? (KH_INV_SQR_BOTH != 0) : (KH_INV_SQR_HASH != 0));
   static constexpr bool PAIRS = (KIND == KH_SCAN_XPOINT) && !ENDO;
   static constexpr bool SHA2TAB = KH_SHA_UNC2_TAB && (KIND == KH_SCAN_UNCOMP || KIND == KH_SCAN_BOTH);   // kernels that stage the table
   const ScanTargets &tg;

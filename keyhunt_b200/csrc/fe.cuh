@@ -474,6 +474,15 @@ static __device__ __noinline__ fe fe_sqr_ol(fe a) {
   return r;
 }
 #endif
+// squaring in a kernel that calls out-of-line copies: the shared multiplier (SQR = false: one copy of code) or the squaring
+template <bool SQR, int RR = KH_RARE_REDUCE>
+KH_HD void fe_sqr_sel(fe &r, const fe &a) {
+#if defined(__CUDA_ARCH__)
+  if (SQR) r = fe_sqr_ol<RR>(a); else r = fe_mul_ol<RR>(a, a);
+#else
+  if (SQR) fe_sqr<RR>(r, a); else fe_mul<RR>(r, a, a);
+#endif
+}
 template <int RR = KH_RARE_REDUCE, bool SQR = false>
 KH_HD void fe_sqr_n_cold(fe &r, const fe &a, int n) {
   r = a;

@@ -330,34 +330,48 @@ KH_HD uint64_t keccak_rc(int r) {
 #endif
 }
 
-KH_HD void keccak_f1600(uint64_t s[25]) {
-#pragma unroll 1
-  for (int r = 0; r < 24; r++) {
-    uint64_t c0 = s[0] ^ s[5] ^ s[10] ^ s[15] ^ s[20];
-    uint64_t c1 = s[1] ^ s[6] ^ s[11] ^ s[16] ^ s[21];
-    uint64_t c2 = s[2] ^ s[7] ^ s[12] ^ s[17] ^ s[22];
-    uint64_t c3 = s[3] ^ s[8] ^ s[13] ^ s[18] ^ s[23];
-    uint64_t c4 = s[4] ^ s[9] ^ s[14] ^ s[19] ^ s[24];
-    uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1), d3 = c2 ^ rotl64(c4, 1),
-             d4 = c3 ^ rotl64(c0, 1);
+KH_HD void keccak_round(uint64_t s[25], uint64_t rc) {
+  uint64_t c0 = s[0] ^ s[5] ^ s[10] ^ s[15] ^ s[20];
+  uint64_t c1 = s[1] ^ s[6] ^ s[11] ^ s[16] ^ s[21];
+  uint64_t c2 = s[2] ^ s[7] ^ s[12] ^ s[17] ^ s[22];
+  uint64_t c3 = s[3] ^ s[8] ^ s[13] ^ s[18] ^ s[23];
+  uint64_t c4 = s[4] ^ s[9] ^ s[14] ^ s[19] ^ s[24];
+  uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1), d3 = c2 ^ rotl64(c4, 1),
+           d4 = c3 ^ rotl64(c0, 1);
 #pragma unroll
-    for (int y = 0; y < 25; y += 5) { s[y] ^= d0; s[y + 1] ^= d1; s[y + 2] ^= d2; s[y + 3] ^= d3; s[y + 4] ^= d4; }
-    // rho + pi
-    uint64_t t = s[1], u;
+  for (int y = 0; y < 25; y += 5) { s[y] ^= d0; s[y + 1] ^= d1; s[y + 2] ^= d2; s[y + 3] ^= d3; s[y + 4] ^= d4; }
+  // rho + pi
+  uint64_t t = s[1], u;
 #define KH_RP(j, n) u = s[j]; s[j] = rotl64(t, n); t = u;
-    KH_RP(10, 1) KH_RP(7, 3) KH_RP(11, 6) KH_RP(17, 10) KH_RP(18, 15) KH_RP(3, 21) KH_RP(5, 28) KH_RP(16, 36)
-    KH_RP(8, 45) KH_RP(21, 55) KH_RP(24, 2) KH_RP(4, 14) KH_RP(15, 27) KH_RP(23, 41) KH_RP(19, 56) KH_RP(13, 8)
-    KH_RP(12, 25) KH_RP(2, 43) KH_RP(20, 62) KH_RP(14, 18) KH_RP(22, 39) KH_RP(9, 61) KH_RP(6, 20) KH_RP(1, 44)
+  KH_RP(10, 1) KH_RP(7, 3) KH_RP(11, 6) KH_RP(17, 10) KH_RP(18, 15) KH_RP(3, 21) KH_RP(5, 28) KH_RP(16, 36)
+  KH_RP(8, 45) KH_RP(21, 55) KH_RP(24, 2) KH_RP(4, 14) KH_RP(15, 27) KH_RP(23, 41) KH_RP(19, 56) KH_RP(13, 8)
+  KH_RP(12, 25) KH_RP(2, 43) KH_RP(20, 62) KH_RP(14, 18) KH_RP(22, 39) KH_RP(9, 61) KH_RP(6, 20) KH_RP(1, 44)
 #undef KH_RP
-    // chi
+  // chi
 #pragma unroll
-    for (int y = 0; y < 25; y += 5) {
-      uint64_t a0 = s[y], a1 = s[y + 1], a2 = s[y + 2], a3 = s[y + 3], a4 = s[y + 4];
-      s[y] = a0 ^ (~a1 & a2); s[y + 1] = a1 ^ (~a2 & a3); s[y + 2] = a2 ^ (~a3 & a4);
-      s[y + 3] = a3 ^ (~a4 & a0); s[y + 4] = a4 ^ (~a0 & a1);
-    }
-    s[0] ^= keccak_rc(r);
+  for (int y = 0; y < 25; y += 5) {
+    uint64_t a0 = s[y], a1 = s[y + 1], a2 = s[y + 2], a3 = s[y + 3], a4 = s[y + 4];
+    s[y] = a0 ^ (~a1 & a2); s[y + 1] = a1 ^ (~a2 & a3); s[y + 2] = a2 ^ (~a3 & a4);
+    s[y + 3] = a3 ^ (~a4 & a0); s[y + 4] = a4 ^ (~a0 & a1);
   }
+  s[0] ^= rc;
+}
+// KH_KECCAK_PEEL: the first and the last round outside the rolled loop.  The compiler then sees the 17 lanes that are zero or
+// constant when the first round starts (the message is 64 bytes: 8 lanes, the padding 2) and that only 3 of the 25 lanes of the
+// last round are output, and drops the work on them
+#ifndef KH_KECCAK_PEEL
+#define KH_KECCAK_PEEL 1
+#endif
+KH_HD void keccak_f1600(uint64_t s[25]) {
+#if KH_KECCAK_PEEL
+  keccak_round(s, keccak_rc(0));
+#pragma unroll 1
+  for (int r = 1; r < 23; r++) keccak_round(s, keccak_rc(r));
+  keccak_round(s, keccak_rc(23));
+#else
+#pragma unroll 1
+  for (int r = 0; r < 24; r++) keccak_round(s, keccak_rc(r));
+#endif
 }
 
 // generate_binaddress_eth (keyhunt.cpp:5663): Keccak-256 (0x01 padding, rate 136) of X||Y

@@ -136,7 +136,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
         fe_add(dym, gy, py);
         fe_mul_sel<OL, RR>(sp, dyp, dinv);
         fe_mul_sel<OL, RR>(sm, dym, dinv);
-        if (OL) { fe_mul_sel<true, RR>(xp, sp, sp); fe_mul_sel<true, RR>(xm, sm, sm); } else { fe_sqr<RR>(xp, sp); fe_sqr<RR>(xm, sm); }
+        if (OL) { fe_sqr_sel<Emit::INV_SQR, RR>(xp, sp); fe_sqr_sel<Emit::INV_SQR, RR>(xm, sm); } else { fe_sqr<RR>(xp, sp); fe_sqr<RR>(xm, sm); }
         fe_add(c, px, gx);
         fe_sub(xp, xp, c);
         fe_sub(xm, xm, c);
@@ -156,7 +156,7 @@ KH_HD void walk_batches(const WalkParams &wp, const uint32_t *tab, uint64_t t, E
           if (sgn == 0 || e == 0) fe_sub(dy, gy, py);   // C + e*S  (and the centre move C + W)
           else fe_add(dy, gy, py);                      // C - e*S : slope is -(gy+py)/dx, its sign is irrelevant for x
           fe_mul_sel<OL, RR>(s, dy, dinv);
-          if (OL) fe_mul_sel<true, RR>(s2, s, s); else fe_sqr<RR>(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
+          if (OL) fe_sqr_sel<Emit::INV_SQR, RR>(s2, s); else fe_sqr<RR>(s2, s);   // dedicated squaring where the FMA-heavy pipe is the bound
           fe_sub(x3, s2, px);
           fe_sub(x3, x3, gx);
           if (e == 0) {                                 // new centre: always needs y
