@@ -59,24 +59,25 @@ STEP_POINTS = 1 << 32
 # ops = the SURVEY constant minus 162 per hashed record: the exact prefix bitmap (emit.cuh prefilter_pass, ~8 ops) answers
 # for the 170-op bloom_check of a non-member, so that work is no longer done and must not be counted as achieved.  Likewise the
 # message schedule of the second SHA-256 block of the uncompressed key (48 words x 10 ops in SURVEY's count) is looked up in a
-# 256-row table since round 2 (hash.cuh KH_SHA_UNC2_TAB) and is not counted: C2 ops = 9950 - 3*162 - 480.
+# 256-row table since round 2 (hash.cuh KH_SHA_UNC2_TAB) and is not counted: C2 ops = 9950 - 3*162 - 480; and the ~270 lane operations that
+# Keccak's peeled first / last round no longer execute (zero input lanes, unused output lanes: hash.cuh KH_KECCAK_PEEL) are not counted for ETH.
 # cpu_rate = expected Mkeys/s per host thread of the reference (only used to size its bounded sample).
 WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
-               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3870),
+               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3888),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
                mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162 - 480, disp=1,
                cpu_rate=1.4, binding="alu",
                alu_ops=6625),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 40.21 G warp instructions per 2^27 points, 69.1 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
                mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, disp=1,
-               cpu_rate=4.8, binding="fma_heavy", wide_mults=251, dram_b_per_point=37.7),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
+               cpu_rate=4.8, binding="fma_heavy", wide_mults=244, dram_b_per_point=37.3),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
                   mode="address", crypto="btc", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5800 - 2 * 162, disp=2,
-                  cpu_rate=2.4, binding="alu", alu_ops=3870),
+                  cpu_rate=2.4, binding="alu", alu_ops=3888),
     "c5eth": dict(desc="C5 address ETH, 1024 targets (16 planted), from 0x10000000000",
-                  mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162, disp=1,
-                  cpu_rate=2.1, binding="alu", alu_ops=5506),
+                  mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162 - 270, disp=1,
+                  cpu_rate=2.1, binding="alu", alu_ops=5268),
 }
 N44 = 1 << 44          # C4: -n 2^44 -k 512 -> m = 2^31 baby steps
 

@@ -400,7 +400,8 @@ int kh_bsgs_build(kh_ctx *c, uint64_t n, uint32_t k) {
       bins.cap = (uint32_t)cap;
       blocks_per_bucket = (uint32_t)((cap + 255) / 256);
       while (n_pass > 1 && (uint64_t)n_buckets * blocks_per_bucket * n_pass >= (1ull << 31)) n_pass--;   // one grid
-      wp.steps = 1;
+      if ((uint64_t)n_buckets * blocks_per_bucket >= (1ull << 31)) { cudaFree(bin_mem); bin_mem = nullptr; memset(&bins, 0, sizeof(bins)); }   // (never with real T)
+      else wp.steps = 1;
     } else {
       cudaGetLastError();
       bin_mem = nullptr;
