@@ -134,6 +134,25 @@ def test_empty_and_duplicate_targets(kh, oracle):
     assert [(h.index, h.key) for h in hits] == [(7, 0x5007)]
 
 
+def test_sorted_and_unsorted_target_sets_give_the_same_tables(kh, oracle):
+    """kh_set_targets sends an already sorted record set to the device as it is (the reference's addressTable arrives sorted) and sorts
+    any other on the host first; either way the words are packed on the device (kh_table_pack): same table, bloom, hits"""
+    rnd = random.Random(77)
+    start = 0x7000000
+    keys = [start + 3, start + 2047]
+    recs = [be32(oracle.pubkey(k)[0])[:20] for k in keys] + [rnd.randbytes(20) for _ in range(3000)]
+    recs += [bytes(20), b"\xff" * 20, recs[5]]                      # extremes and a duplicate
+    seen = []
+    for order in (sorted(recs), recs, sorted(recs, reverse=True)):
+        kh.set_targets(K.MODE_XPOINT, b"".join(order))
+        d, bits = kh.get_bloom()
+        kh.scan(start, 4096)
+        seen.append((kh.get_table(), d.as_dict(), bits, [(h.index, h.key) for h in kh.poll_hits()]))
+    assert seen[0][0] == b"".join(sorted(recs))
+    assert seen[0] == seen[1] == seen[2]
+    assert seen[0][3] == [(3, keys[0]), (2047, keys[1])]
+
+
 def test_hit_buffer_overflow_is_reported(kh, oracle):
     """every point of the range is a target: more hits than the device hit buffer holds -> KH_EOVERFLOW (loud, not silent)"""
     start, n = 0x7000, 2048
