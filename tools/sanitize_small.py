@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Small end-to-end pass over every kernel family, sized for compute-sanitizer (memcheck / racecheck / initcheck):
-   compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Small end-to-end pass over every kernel family (five scan kinds with planted keys, direct and binned / sliced BSGS builds with
+their digests, a BSGS search), sized so that it also finishes under compute-sanitizer where that tool is available:
+   [compute-sanitizer --tool memcheck] python tools/sanitize_small.py"""
 import os, random, sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import keyhunt_b200 as K
