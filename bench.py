@@ -64,19 +64,19 @@ STEP_POINTS = 1 << 32
 # cpu_rate = expected Mkeys/s per host thread of the reference (only used to size its bounded sample).
 WORKLOADS = {
     "c1": dict(desc="C1 address compress, tests/1to32 puzzle targets", mode="address", crypto="btc", search="compress",
-               start=0x1, n_targets=32, ops=5800 - 2 * 162, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3888),
+               start=0x1, n_targets=32, ops=5800 - 2 * 162, survey_ops=5800, disp=2, cpu_rate=2.4, binding="alu", alu_ops=3888),
     "c2": dict(desc="C2 rmd160 -l both, 1024 hash160 targets (24 planted), 2^36 keys from 0x2000000000000000",
-               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162 - 480, disp=1,
+               mode="rmd160", crypto="btc", search="both", start=0x2000000000000000, n_targets=1024, planted=24, ops=9950 - 3 * 162 - 480, survey_ops=9950, disp=1,
                cpu_rate=1.4, binding="alu",
                alu_ops=6625),   # executed ALU-pipe thread instructions per point, from the ncu source page (profiles/r02_both_opmix.txt: 40.21 G warp instructions per 2^27 points, 69.1 % of them SHF/LOP3/IADD3/LEA/...); likewise for the other kinds
     "c3": dict(desc="C3 xpoint, 10^6 x-coordinates (32 planted), 2^36 keys from 0x4000000000000000",
-               mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, disp=1,
+               mode="xpoint", crypto="btc", search="compress", start=0x4000000000000000, n_targets=1000000, planted=32, ops=900 - 162, survey_ops=900, disp=1,
                cpu_rate=4.8, binding="fma_heavy", wide_mults=244, dram_b_per_point=37.3),   # executed IMAD.WIDE per point (profiles/r02_xpoint_opmix.txt; 2.5 M + 1 S = 224 of them, the rest is bloom/bitmap index arithmetic)
     "c5btc": dict(desc="C5 address BTC compress, 1024 targets (16 planted), from 0x10000000000",
-                  mode="address", crypto="btc", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5800 - 2 * 162, disp=2,
+                  mode="address", crypto="btc", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5800 - 2 * 162, survey_ops=5800, disp=2,
                   cpu_rate=2.4, binding="alu", alu_ops=3888),
     "c5eth": dict(desc="C5 address ETH, 1024 targets (16 planted), from 0x10000000000",
-                  mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162 - 270, disp=1,
+                  mode="address", crypto="eth", search="compress", start=0x10000000000, n_targets=1024, planted=16, ops=5930 - 162 - 270, survey_ops=5930, disp=1,
                   cpu_rate=2.1, binding="alu", alu_ops=5268),
 }
 N44 = 1 << 44          # C4: -n 2^44 -k 512 -> m = 2^31 baby steps
@@ -428,6 +428,9 @@ def roofline(env, wl, value_pts_s, pts_per_launch, launch_ms, clk):
          "traffic": w.get("dram_b_per_point", 32.0) * pts_per_launch,
          "traffic_unit": "bytes of DRAM read+write per launch (ncu-measured %.1f B/point x points per launch)" % w.get("dram_b_per_point", 32.0),
          "kernel": "kh_scan_kernel", "ops_per_point": w["ops"], "launch_ms": launch_ms,
+         # `achieved` / `frac` count only the work the kernel still DOES (SURVEY's constant minus what the prefix bitmap, the SHA-256 schedule
+         # table and the peeled Keccak rounds made unnecessary); with SURVEY §8d's undiscounted per-point figure the fraction would be:
+         "ops_per_point_survey": w["survey_ops"], "frac_survey_ops": achieved * w["survey_ops"] / w["ops"] / peak,
          "peak_source": "measured live: kh_int_peak LOP3+IMAD dual-pipe rate; ALU pipe alone %.2f, IMAD %.2f, IMAD.WIDE %.2f Tiop/s"
                         % (peaks["lop3"] / 1e12, peaks["imad"] / 1e12, peaks["imad_wide"] / 1e12),
          "frac_of_nominal_64_lanes": achieved / nominal, "nominal_peak": nominal,
