@@ -89,6 +89,18 @@ def test_r02_strong_scaling_on_two_gpus():
     assert d2["strong"]["c4"]["planted"]["planted_found"] is True
 
 
+def test_r02_rerun_carries_the_undiscounted_fraction():
+    """bench.py reports the roofline fraction against the work the kernel still does AND against SURVEY's undiscounted per-point figure"""
+    d1, d = _line(R02), _line(os.path.join(ROOT, "profiles", "r02_bench_n1_rerun.json"))
+    assert abs(d["value"] - d1["value"]) / d1["value"] < 0.02                      # another box, same build
+    r = d["roofline"]
+    assert r["ops_per_point_survey"] == 9950 and r["ops_per_point"] == 9950 - 3 * 162 - 480
+    assert abs(r["frac_survey_ops"] - r["frac"] * 9950 / r["ops_per_point"]) < 1e-9 and r["frac"] < r["frac_survey_ops"] < 1
+    for name in ("c1", "c3", "c5btc", "c5eth"):
+        x = d["workloads"][name]["roofline"]
+        assert x["frac"] <= x["frac_survey_ops"] < 1, name
+
+
 def test_r02_eight_gpus():
     """one 8 x B200 node (gpurun --gpus 8, tools/gpu_job_n8.sh): weak-scaled headline and the strong-scaling blocks"""
     d1, d8 = _line(R02), _line(os.path.join(ROOT, "profiles", "r02_bench_n8.json"))
