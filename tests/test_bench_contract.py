@@ -101,6 +101,14 @@ def test_r02_rerun_carries_the_undiscounted_fraction():
         assert x["frac"] <= x["frac_survey_ops"] < 1, name
 
 
+def test_r02_four_gpus():
+    d1, d4 = _line(R02), _line(os.path.join(ROOT, "profiles", "r02_bench_n4.json"))
+    assert d4["n_gpus"] == 4 and d4["hits"]["all_planted_found_and_nothing_else"] is True and 3.9 < d4["value"] / d1["value"] < 4.1
+    for cur in ("c5btc", "c5eth"):
+        assert d4["strong"]["c5"][cur]["planted_found_and_nothing_else"] is True and d4["strong"]["c5"][cur]["efficiency"] > 0.95
+    assert d4["strong"]["c4"]["sweep"]["efficiency"] > 0.9 and d4["strong"]["c4"]["planted"]["planted_found"] is True
+
+
 def test_r02_eight_gpus():
     """one 8 x B200 node (gpurun --gpus 8, tools/gpu_job_n8.sh): weak-scaled headline and the strong-scaling blocks"""
     d1, d8 = _line(R02), _line(os.path.join(ROOT, "profiles", "r02_bench_n8.json"))
